@@ -110,8 +110,8 @@ def make_sequence(seed: int, num_steps: int, num_envs: int, device: str = "cpu",
     return StateSequence(dof_state, root_state, rigid_body.contiguous(), dof_force, ft_sensors, action)
 
 
-def plant_edge_cases(seq: StateSequence, goal_pose: torch.Tensor) -> None:
-    """Overwrite the first envs of every step with the edge cases of SURVEY.md §A.7.
+def plant_edge_cases(seq: StateSequence, goal_pose: torch.Tensor, first_step: int = 1) -> None:
+    """Overwrite the first envs of every step >= first_step with the edge cases of SURVEY.md §A.7.
 
     `goal_pose` [N,7] is the goal the envs will hold (the caller forces it into
     the goal buffer).  env 0: object quat == goal quat; env 1: antipodal quat;
@@ -123,7 +123,7 @@ def plant_edge_cases(seq: StateSequence, goal_pose: torch.Tensor) -> None:
     N = seq.num_envs
     assert N >= 8
     root = seq.root_state.view(seq.num_steps, N, NUM_ACTORS, ROW)
-    obj = root[:, :, OBJECT_SLOT]
+    obj = root[first_step:, :, OBJECT_SLOT]
     obj[:, 0, 3:7] = goal_pose[0, 3:7]
     obj[:, 1, 3:7] = -goal_pose[1, 3:7]
     obj[:, 2, 3:7] = torch.tensor([1.5, -0.7, 0.9, 0.1])
@@ -132,7 +132,7 @@ def plant_edge_cases(seq: StateSequence, goal_pose: torch.Tensor) -> None:
     obj[:, 5, 0:3] = goal_pose[5, 0:3]
     obj[:, 5, 0] += 0.01
     for b in FINGERTIP_BODIES:
-        seq.rigid_body[:, 6, b, 0:3] = obj[:, 6, 0:3]
+        seq.rigid_body[first_step:, 6, b, 0:3] = obj[:, 6, 0:3]
 
 
 def bernoulli_masks(seed: int, num_steps: int, num_envs: int, p: float,

@@ -1,0 +1,110 @@
+"""Uniform test-side view of an env (oracle or CUDA) for the golden replay."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle.trifinger_oracle import OracleEnv, OracleSim
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+class _CapturingSim(OracleSim):
+    def simulate(self):
+        self.pre_sim_dof = self.dof.clone()
+        self.pre_sim_root = self.root.clone()
+        super().simulate()
+
+
+class OracleAdapter:
+    """OracleEnv behind the reference's attribute names."""
+
+    def __init__(self, config, seq):
+        from leibnizgym_b200.config import resolve_config
+        self.cfg = resolve_config(config)
+        self.N = self.cfg["num_instances"]
+        self.sim = _CapturingSim(seq, self.N)
+        self.env = OracleEnv(self.cfg, self.sim)
+
+    # reference-style buffer names used by the replay driver
+    @property
+    def _reset_buf(self):
+        return self.env.reset_buf
+
+    @_reset_buf.setter
+    def _reset_buf(self, v):
+        self.env.reset_buf = v
+
+    @property
+    def _goal_reset_buf(self):
+        return self.env.goal_reset_buf
+
+    @_goal_reset_buf.setter
+    def _goal_reset_buf(self, v):
+        self.env.goal_reset_buf = v
+
+    def inject_draws(self, reset=None, goal=None):
+        self.env.inject_draws(reset=reset, goal=goal)
+
+    def reset(self):
+        self.env.index_lists = {}
+        self.env.last_ids = (torch.arange(self.N), torch.zeros(0, dtype=torch.long))
+        return self.env.reset()
+
+    def step(self, action):
+        self.env.index_lists = {}
+        return self.env.step(action)
+
+    def observe(self, key):
+        e, s, N = self.env, self.sim, self.N
+        if key == "reset_in":
+            return _np(e.reset_buf)
+        if key == "goal_reset_in":
+            return _np(e.goal_reset_buf)
+        if key == "reset_ids":
+            return _np(e.last_ids[0])
+        if key == "goal_reset_ids":
+            return _np(e.last_ids[1])
+        if key == "pre_sim_dof":
+            return _np(s.pre_sim_dof)
+        if key == "pre_sim_obj_root":
+            return _np(s.pre_sim_root.view(N, 4, 13)[:, 2])
+        if key == "pre_sim_goal_root":
+            return _np(s.pre_sim_root.view(N, 4, 13)[:, 3])
+        if key == "dof_index_list":
+            return _np(e.index_lists["dof"])
+        if key == "root_index_list0":
+            return _np(e.index_lists["root_reset"] if "root_reset" in e.index_lists else e.index_lists["root_goal"])
+        if key == "root_index_list1":
+            return _np(e.index_lists["root_goal"])
+        if key == "applied_torque":
+            return _np(e.applied_torque)
+        if key == "goal_pose":
+            return _np(e.goal_poses)
+        if key == "goal_movement":
+            return _np(e.goal_movement)
+        if key == "action_buf":
+            return _np(e.action_buf)
+        if key == "obs":
+            return _np(e.obs_buf)
+        if key == "states":
+            return _np(e.states_buf)
+        if key == "reset_buf":
+            return _np(e.reset_buf)
+        if key == "goal_reset_buf":
+            return _np(e.goal_reset_buf)
+        if key == "steps_count":
+            return _np(e.steps_count_buf)
+        if key == "successes":
+            return _np(e.successes)
+        if key == "terms":
+            return _np(e.last_terms)
+        if key == "reward":
+            return _np(e.reward_buf)
+        if key == "sched_step":
+            return np.asarray(e.env_steps_count)
+        if key == "info":
+            return {k: float(v) for k, v in e.step_info.items()}
+        raise KeyError(key)
