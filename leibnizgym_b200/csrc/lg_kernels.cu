@@ -1,0 +1,855 @@
+// sm_100a kernels + C ABI of the TriFinger MDP hot path (see include/leibniz_b200.h).
+//
+// Two launches per env step, both env-major and HBM-bound (no tensor cores: the path is
+// elementwise, ~2 FLOP/B):
+//   pre_physics_kernel   ordered mask compaction (decoupled look-back) + reset / goal-reset
+//                        sampling and scatter + action store + action->torque
+//   post_physics_kernel  obs/states fill + scale_transform, six reward terms, termination,
+//                        step counters / timeouts / dones, episode statistics
+// Reference paths are relative to /root/reference/leibnizgym/.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "lg_device.cuh"
+
+namespace lg {
+
+// =========================================================================================
+// post-physics: one CTA = one tile of kTileEnvs envs, kSubs threads per env
+// =========================================================================================
+constexpr int kTileEnvs = 32;
+constexpr int kSubs = 4;
+constexpr int kPostThreads = kTileEnvs * kSubs;  // 128
+
+template <int A, bool ASYM>
+struct Layout {
+  static constexpr int OBS = 32 + A;              // q 9 | qdot 9 | object pose 7 | goal pose 7 | action A
+  static constexpr int STATE = OBS + 72;          // + object vel 6 | fingertips 39 | torque 9 | wrench 18
+  static constexpr int ROW = ASYM ? STATE : OBS;  // floats per env in the staged tile
+  static constexpr int OFF_OBJ = 18, OFF_GOAL = 25, OFF_ACT = 32;
+  static constexpr int OFF_OBJVEL = OBS, OFF_TIPS = OBS + 6, OFF_TORQUE = OBS + 45, OFF_FT = OBS + 54;
+};
+
+// coefficient slots computed once per CTA (python-float arithmetic of the reward modules)
+enum Coef { C_REACH = 0, C_MOVE, C_DIST, C_ROT_SCALE, C_ROT_SCHED, C_ROT_W, C_DELTA_RAMP, C_DELTA_W,
+            C_OBJMOVE, C_DT, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_COUNT };
+
+__device__ __forceinline__ double sched_gate(const LgRewardTerm& t, double T) {  // rewards.py:56-60
+  if (t.sched_start != t.sched_end) return (t.sched_start <= T && T <= t.sched_end) ? 1.0 : 0.0;
+  return 1.0;
+}
+__device__ __forceinline__ double sched_ramp(const LgRewardTerm& t, double T) {  // rewards.py:14-17, :169-172
+  if (t.sched_start != t.sched_end) {
+    const double v = (T - t.sched_start) / (t.sched_end - t.sched_start);
+    return fmax(0.0, fmin(1.0, v));
+  }
+  return 1.0;
+}
+
+// cooperative tile load: 128-bit streaming loads over the contiguous slab, scalar tail
+template <typename Sink>
+__device__ __forceinline__ void slab_load(const float* __restrict__ src, int nfloats, Sink&& sink) {
+  const int n4 = nfloats >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+    const float4 v = ld_stream4(s4 + j);
+    sink(4 * j, v.x); sink(4 * j + 1, v.y); sink(4 * j + 2, v.z); sink(4 * j + 3, v.w);
+  }
+  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += blockDim.x) sink(i, ld_stream1(src + i));
+}
+
+// cooperative tile store: Source(i) yields float i of the slab
+template <typename Source>
+__device__ __forceinline__ void slab_store(float* __restrict__ dst, int nfloats, Source&& src) {
+  const int n4 = nfloats >> 2;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+    float4 v;
+    v.x = src(4 * j); v.y = src(4 * j + 1); v.z = src(4 * j + 2); v.w = src(4 * j + 3);
+    st_stream4(d4 + j, v);
+  }
+  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src(i);
+}
+
+template <int A, bool ASYM, bool REWARD>
+__global__ void __launch_bounds__(kPostThreads)
+post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B, double sched_step_host) {
+  using L = Layout<A, ASYM>;
+  constexpr int E = kTileEnvs;
+  __shared__ __align__(16) float s_raw[E * L::ROW];       // raw (unscaled) obs/state rows, state order
+  __shared__ __align__(16) float s_hist[E * LG_HISTORY_COLS];
+  __shared__ float s_tips[ASYM ? 1 : E * 9];               // symmetric mode: current fingertip positions
+  __shared__ float s_centre[L::ROW], s_span[L::ROW];
+  __shared__ float s_coef[C_COUNT];
+  __shared__ double s_red[kPostThreads / 32][LG_NUM_STATS];
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int64_t e0 = (int64_t)blockIdx.x * E;
+  const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
+
+  // ---- per-CTA scalars -------------------------------------------------------------
+  for (int c = tid; c < L::ROW; c += kPostThreads) { s_centre[c] = P.scale_centre[c]; s_span[c] = P.scale_span[c]; }
+  if (REWARD && tid == 0) {
+    const double T = P.use_device_clock ? (double)(B.control->frame_count * P.global_num_envs) : sched_step_host;
+    const LgRewardTerm* t = P.terms;
+    s_coef[C_REACH] = (float)(t[0].weight * sched_gate(t[0], T));             // rewards.py:235
+    s_coef[C_MOVE] = (float)t[1].weight;                                       // rewards.py:263
+    s_coef[C_DIST] = (float)((t[2].weight * P.dt) * sched_gate(t[2], T));     // rewards.py:63
+    s_coef[C_ROT_SCALE] = (float)t[3].scale;                                   // rewards.py:137
+    s_coef[C_ROT_SCHED] = (float)(sched_gate(t[3], T) * P.dt);
+    s_coef[C_ROT_W] = (float)t[3].weight;                                      // rewards.py:139
+    s_coef[C_DELTA_RAMP] = (float)sched_ramp(t[4], T);                         // rewards.py:182
+    s_coef[C_DELTA_W] = (float)t[4].weight;                                    // rewards.py:184
+    s_coef[C_OBJMOVE] = (float)t[5].weight;                                    // rewards.py:91
+    s_coef[C_DT] = (float)P.dt;
+    s_coef[C_POS_TOL] = (float)P.position_tolerance;
+    s_coef[C_ROT_TOL] = (float)P.orientation_tolerance;
+    s_coef[C_BONUS] = (float)P.success_bonus;
+    s_coef[C_KP_W] = (float)(t[6].weight * P.dt);
+    s_coef[C_KP_SCALE] = (float)t[6].scale;
+    s_coef[C_KP_EPS] = (float)t[6].eps;
+  }
+
+  // ---- stage the tile: contiguous slabs with 128-bit loads -------------------------------
+  // dof_state [N,9,2] -> q (cols 0:9), qdot (cols 9:18)        trifinger_env.py:1003-1007
+  slab_load(S.dof_state + e0 * 18, nvalid * 18, [&](int i, float v) {
+    const int env = i / 18, r = i - env * 18;
+    s_raw[env * L::ROW + (r & 1) * 9 + (r >> 1)] = v;
+  });
+  // goal pose buffer -> cols 25:32                              trifinger_env.py:1015
+  slab_load(B.goal_pose + e0 * 7, nvalid * 7, [&](int i, float v) {
+    const int env = i / 7;
+    s_raw[env * L::ROW + L::OFF_GOAL + (i - env * 7)] = v;
+  });
+  // last action -> cols 32:32+A                                 trifinger_env.py:1019
+  slab_load(B.action + e0 * A, nvalid * A, [&](int i, float v) {
+    const int env = i / A;
+    s_raw[env * L::ROW + L::OFF_ACT + (i - env * A)] = v;
+  });
+  // previous fingertip positions + previous object pose (history entry 1)
+  slab_load(B.history + e0 * LG_HISTORY_COLS, nvalid * LG_HISTORY_COLS, [&](int i, float v) { s_hist[i] = v; });
+  if (ASYM) {
+    slab_load(S.dof_force + e0 * 9, nvalid * 9, [&](int i, float v) {      // trifinger_env.py:1047
+      const int env = i / 9;
+      s_raw[env * L::ROW + L::OFF_TORQUE + (i - env * 9)] = v;
+    });
+    slab_load(S.ft_sensors + e0 * 18, nvalid * 18, [&](int i, float v) {   // trifinger_env.py:1051
+      const int env = i / 18;
+      s_raw[env * L::ROW + L::OFF_FT + (i - env * 18)] = v;
+    });
+  }
+  // ---- gathers: 52-byte rows out of the simulator tensors, consecutive lanes on consecutive floats
+  {
+    // object root row (actor 4e+2): pose -> cols 18:25, velocity -> state cols OBS:OBS+6   :975, :1011, :1035
+    constexpr int OBJ_COLS = ASYM ? 13 : 7;
+    for (int i = tid; i < nvalid * OBJ_COLS; i += kPostThreads) {
+      const int env = i / OBJ_COLS, c = i - env * OBJ_COLS;
+      const float v = ld_stream1(S.root_state + ((int64_t)P.actors_per_env * (e0 + env) + P.object_slot) * 13 + c);
+      s_raw[env * L::ROW + (c < 7 ? L::OFF_OBJ + c : L::OFF_OBJVEL + (c - 7))] = v;
+    }
+    // fingertip rows (bodies 6/11/16): full 13-float states when asymmetric, positions only otherwise  :974, :1040
+    constexpr int TIP_COLS = ASYM ? 13 : 3;
+    for (int i = tid; i < nvalid * 3 * TIP_COLS; i += kPostThreads) {
+      const int env = i / (3 * TIP_COLS), r = i - env * (3 * TIP_COLS);
+      const int tip = r / TIP_COLS, c = r - tip * TIP_COLS;
+      const float v = ld_stream1(S.rigid_body + ((e0 + env) * P.bodies_per_env + P.fingertip_body[tip]) * 13 + c);
+      if (ASYM) s_raw[env * L::ROW + L::OFF_TIPS + r] = v;
+      else s_tips[env * 9 + r] = v;
+    }
+  }
+  __syncthreads();
+
+  auto tip_pos = [&](int env, int tip, int c) -> float {
+    return ASYM ? s_raw[env * L::ROW + L::OFF_TIPS + tip * 13 + c] : s_tips[env * 9 + tip * 3 + c];
+  };
+
+  // ---- rewards / termination: 4 lanes per env, each one sub-task, combined by shuffles ---------
+  if (REWARD) {
+    const int env = tid >> 2, sub = tid & 3;
+    const bool live = env < nvalid;
+    const float* row = s_raw + env * L::ROW;
+    const float* hist = s_hist + env * LG_HISTORY_COLS;
+    float va = 0.0f, vb = 0.0f, vc = 0.0f, vd = 0.0f;  // sub-task results
+    if (live) {
+      const float ox = row[L::OFF_OBJ], oy = row[L::OFF_OBJ + 1], oz = row[L::OFF_OBJ + 2];
+      const float gx = row[L::OFF_GOAL], gy = row[L::OFF_GOAL + 1], gz = row[L::OFF_GOAL + 2];
+      const Quat gq{row[L::OFF_GOAL + 3], row[L::OFF_GOAL + 4], row[L::OFF_GOAL + 5], row[L::OFF_GOAL + 6]};
+      if (sub == 0) {
+        // finger_reach_object_rate (rewards.py:219-235): sum_i (|tip_i - obj| - |tip_i' - obj'|)
+        const float px = hist[9], py = hist[10], pz = hist[11];
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float cur = norm3(tip_pos(env, i, 0) - ox, tip_pos(env, i, 1) - oy, tip_pos(env, i, 2) - oz);
+          const float prev = norm3(hist[3 * i] - px, hist[3 * i + 1] - py, hist[3 * i + 2] - pz);
+          acc = acc + (cur - prev);
+        }
+        va = s_coef[C_REACH] * acc;
+      } else if (sub == 1) {
+        // finger_move_penalty (rewards.py:261-263): sum_9 ((tip - tip') / dt)^2
+        const float dt = s_coef[C_DT];
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = __fdiv_rn(tip_pos(env, i, c) - hist[3 * i + c], dt);
+            acc = acc + v * v;
+          }
+        va = s_coef[C_MOVE] * acc;
+        // object_dist (rewards.py:62-63) and object_move (rewards.py:88-91)
+        const float d = norm3(ox - gx, oy - gy, oz - gz);
+        const float dprev = norm3(hist[9] - gx, hist[10] - gy, hist[11] - gz);
+        vb = lgsk(d, 50.0f) * s_coef[C_DIST];
+        vc = s_coef[C_OBJMOVE] * (d - dprev);
+        vd = d;
+      } else if (sub == 2) {
+        // object_rot (rewards.py:134-139): w * (gate*dt) / (scale*|theta| + scale)
+        const Quat oq{row[L::OFF_OBJ + 3], row[L::OFF_OBJ + 4], row[L::OFF_OBJ + 5], row[L::OFF_OBJ + 6]};
+        const float theta = quat_diff_rad(oq, gq);
+        const float den = s_coef[C_ROT_SCALE] * fabsf(theta) + s_coef[C_ROT_SCALE];
+        va = (__frcp_rn(den) * s_coef[C_ROT_SCHED]) * s_coef[C_ROT_W];
+        vb = theta;
+      } else {
+        // previous-orientation angle for object_rot_delta (rewards.py:179)
+        const Quat pq{hist[12], hist[13], hist[14], hist[15]};
+        vb = fabsf(quat_diff_rad(pq, gq));
+      }
+    }
+    // gather the sub-results onto lane sub==0 of each env
+    const unsigned full = 0xffffffffu;
+    const int base = (tid & 31) & ~3;
+    const float t_move = __shfl_sync(full, va, base + 1);
+    const float t_dist = __shfl_sync(full, vb, base + 1);
+    const float t_objmove = __shfl_sync(full, vc, base + 1);
+    const float dist = __shfl_sync(full, vd, base + 1);
+    const float t_rot = __shfl_sync(full, va, base + 2);
+    const float theta = __shfl_sync(full, vb, base + 2);
+    const float theta_prev_abs = __shfl_sync(full, vb, base + 3);
+
+    double st[LG_NUM_STATS];
+#pragma unroll
+    for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0;
+    if (live && sub == 0) {
+      const int64_t e = e0 + env;
+      const float t_reach = va;
+      // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
+      const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - theta_prev_abs));
+      const float terms[6] = {t_reach, t_move, t_dist, t_rot, t_delta, t_objmove};
+      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (P.terms[k].activate) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = (double)terms[k]; }
+        if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
+      }
+      // __check_termination (trifinger_env.py:1053-1099)
+      const bool pos_ok = dist <= s_coef[C_POS_TOL];
+      const bool rot_ok = theta <= s_coef[C_ROT_TOL];
+      bool done;
+      if (P.task_difficulty < 4) done = pos_ok;
+      else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
+      else done = rot_ok;
+      bool goal_reset = B.goal_reset[e] != 0;
+      bool succ = B.successes[e] != 0;
+      if (P.success_activate) {
+        if (done) reward = reward + s_coef[C_BONUS];
+        goal_reset = done;
+        succ = succ || goal_reset;
+        B.goal_reset[e] = goal_reset;
+      } else {
+        succ = goal_reset && succ;
+      }
+      B.successes[e] = succ;
+      B.reward[e] = reward;
+      // step counter, timeout, dones (envs/env_base.py:391-399)
+      bool reset = B.reset[e] != 0;
+      if (P.fuse_bookkeeping) {
+        const int64_t steps = B.steps_count[e] + 1;
+        B.steps_count[e] = steps;
+        if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
+        B.reset[e] = reset;
+      }
+      const bool dn = reset && goal_reset;
+      if (B.dones) B.dones[e] = dn;
+      st[LG_STAT_POSITION_GOAL] = pos_ok;
+      st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
+      st[LG_STAT_SUCCESSES] = succ;
+      st[LG_STAT_REWARD] = (double)reward;
+      st[LG_STAT_RESETS] = reset;
+      st[LG_STAT_DONES] = dn;
+    }
+    // episode statistics: fp64 warp tree over the 8 env-leader lanes, then one RED per slot per CTA
+#pragma unroll
+    for (int i = 0; i < LG_NUM_STATS; ++i) {
+      if (i == 6 || i > LG_STAT_DONES) continue;  // keypoint slot / unused
+      double v = st[i];
+      v += __shfl_xor_sync(full, v, 4);
+      v += __shfl_xor_sync(full, v, 8);
+      v += __shfl_xor_sync(full, v, 16);
+      if ((tid & 31) == 0) s_red[tid >> 5][i] = v;
+    }
+  }
+
+  // ---- outputs: scale_transform (torch_utils.py:33-36) fused into 128-bit slab stores -----------
+  const bool norm = P.normalize_obs != 0;
+  auto scaled = [&](int env, int c) -> float {
+    const float v = s_raw[env * L::ROW + c];
+    return norm ? scale_transform(v, s_centre[c], s_span[c]) : v;
+  };
+  const float clip = P.clip_obs;
+  slab_store(B.obs + e0 * L::OBS, nvalid * L::OBS, [&](int i) {          // trifinger_env.py:983-987
+    const int env = i / L::OBS;
+    return scaled(env, i - env * L::OBS);
+  });
+  if (B.obs_clipped)
+    slab_store(B.obs_clipped + e0 * L::OBS, nvalid * L::OBS, [&](int i) {  // wrappers/vec_task.py:167
+      const int env = i / L::OBS;
+      return fminf(fmaxf(scaled(env, i - env * L::OBS), -clip), clip);
+    });
+  if (ASYM) {
+    slab_store(B.states + e0 * L::STATE, nvalid * L::STATE, [&](int i) {  // trifinger_env.py:990-994
+      const int env = i / L::STATE;
+      return scaled(env, i - env * L::STATE);
+    });
+    if (B.states_clipped)
+      slab_store(B.states_clipped + e0 * L::STATE, nvalid * L::STATE, [&](int i) {  // vec_task.py:147
+        const int env = i / L::STATE;
+        return fminf(fmaxf(scaled(env, i - env * L::STATE), -clip), clip);
+      });
+  }
+  // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step
+  slab_store(B.history + e0 * LG_HISTORY_COLS, nvalid * LG_HISTORY_COLS, [&](int i) {
+    const int env = i >> 4, c = i & 15;
+    return c < 9 ? tip_pos(env, c / 3, c % 3) : s_raw[env * L::ROW + L::OFF_OBJ + (c - 9)];
+  });
+
+  // ---- statistics epilogue: the last CTA to finish publishes sums and `_step_info` --------------
+  if (REWARD) {
+    __syncthreads();
+    if (tid < LG_NUM_STATS) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kPostThreads / 32; ++w) v += s_red[w][tid];
+      if (!(tid == 6 || tid > LG_STAT_DONES)) atomicAdd(B.stats_accum + tid, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_is_last = (atomicAdd(&B.control->post_done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_is_last) {
+      __threadfence();
+      if (tid < LG_NUM_STATS) {
+        const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(B.stats_accum + tid), 0ull);
+        const double v = __longlong_as_double((long long)bits);
+        B.stats[tid] = v;
+        // reward-term and success entries are means (trifinger_env.py:554, :1098), the rest counts (:1067, :1076)
+        const bool is_mean = tid < LG_STAT_POSITION_GOAL || tid == LG_STAT_SUCCESSES || tid == LG_STAT_REWARD;
+        B.step_info[tid] = is_mean ? (float)(v / (double)P.num_envs) : (float)v;
+      }
+      if (tid == 0) {
+        B.control->post_done = 0;
+        B.control->rng_epoch += 1;  // fresh random numbers for the next step's resets
+      }
+    }
+  }
+}
+
+// history seeding (trifinger_env.py:619-628): both entries = initial simulator state
+__global__ void init_history_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.num_envs * LG_HISTORY_COLS) return;
+  const int64_t e = i >> 4;
+  const int c = (int)(i & 15);
+  float v;
+  if (c < 9) v = S.rigid_body[(e * P.bodies_per_env + P.fingertip_body[c / 3]) * 13 + (c % 3)];
+  else v = S.root_state[((int64_t)P.actors_per_env * e + P.object_slot) * 13 + (c - 9)];
+  B.history[i] = v;
+}
+
+// =========================================================================================
+// pre-physics: ordered compaction by decoupled look-back, fused with the resets
+// =========================================================================================
+constexpr int kPreThreads = 128;  // one env per thread, one tile per CTA
+
+// status word: [63:48] epoch | [47:46] state | [45:23] count A | [22:0] count B
+constexpr uint64_t kStateAggregate = 1, kStateInclusive = 2;
+__device__ __forceinline__ uint64_t pack_status(uint32_t epoch, uint64_t state, uint32_t a, uint32_t b) {
+  return ((uint64_t)(epoch & 0xffffu) << 48) | (state << 46) | ((uint64_t)(a & 0x7fffffu) << 23) | (uint64_t)(b & 0x7fffffu);
+}
+__device__ __forceinline__ bool status_valid(uint64_t w, uint32_t epoch) {
+  return (uint32_t)(w >> 48) == (epoch & 0xffffu) && ((w >> 46) & 3u) != 0;
+}
+
+// Exclusive prefix of (a, b) over all tiles before `tile`; executed by the first warp of the CTA.
+__device__ __forceinline__ void lookback(uint64_t* status, int tile, uint32_t epoch, uint32_t my_a, uint32_t my_b,
+                                         uint32_t& ex_a, uint32_t& ex_b) {
+  const int lane = threadIdx.x & 31;
+  uint32_t acc_a = 0, acc_b = 0;
+  int pos = tile - 1;
+  while (pos >= 0) {
+    const int idx = pos - lane;
+    uint64_t w = 0;
+    bool ok;
+    do {
+      ok = true;
+      if (idx >= 0) { w = ld_volatile_u64(status + idx); ok = status_valid(w, epoch); }
+    } while (__any_sync(0xffffffffu, !ok));
+    const bool incl = idx >= 0 && ((w >> 46) & 3u) == kStateInclusive;
+    const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
+    const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;  // nearest predecessor holding an inclusive prefix
+    uint32_t a = (idx >= 0 && lane <= stop) ? (uint32_t)((w >> 23) & 0x7fffffu) : 0u;
+    uint32_t b = (idx >= 0 && lane <= stop) ? (uint32_t)(w & 0x7fffffu) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    acc_a += a; acc_b += b;
+    if (incl_mask) break;
+    pos -= 32;
+  }
+  ex_a = acc_a; ex_b = acc_b;
+  if (lane == 0) {
+    __threadfence();
+    atomicExch(reinterpret_cast<unsigned long long*>(status + tile),
+               (unsigned long long)pack_status(epoch, kStateInclusive, acc_a + my_a, acc_b + my_b));
+  }
+}
+
+struct TileScan {
+  int tile;
+  uint32_t epoch;
+  uint32_t rank_a, rank_b;   // this thread's rank inside the tile (valid where its flag is set)
+  uint32_t total_a, total_b; // tile totals
+};
+
+// Resolves the global exclusive prefix; the last tile re-arms ticket and epoch for the next launch.
+__device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* status, const TileScan& t, int num_tiles,
+                                                 uint32_t& ex_a, uint32_t& ex_b, int32_t* counts_out) {
+  __shared__ uint32_t s_ex[2];
+  if (threadIdx.x < 32) {
+    uint32_t a = 0, b = 0;
+    if (t.tile > 0) lookback(status, t.tile, t.epoch, t.total_a, t.total_b, a, b);
+    if (threadIdx.x == 0) {
+      s_ex[0] = a; s_ex[1] = b;
+      if (t.tile == num_tiles - 1) {
+        // every tile has read the epoch and taken its ticket by now (their aggregates are visible)
+        if (counts_out) { counts_out[0] = (int32_t)(a + t.total_a); counts_out[1] = (int32_t)(b + t.total_b); }
+        ctl->scan_ticket = 0;
+        __threadfence();
+        ctl->scan_epoch = t.epoch + 1;
+      }
+    }
+  }
+  __syncthreads();
+  ex_a = s_ex[0]; ex_b = s_ex[1];
+}
+
+__global__ void __launch_bounds__(kPreThreads)
+pre_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B,
+                   const float* __restrict__ action_in, int num_tiles) {
+  const int tid = threadIdx.x;
+  // tiles are handed out by ticket so that every predecessor of a tile is already running
+  __shared__ int s_tile;
+  __shared__ uint32_t s_epoch;
+  if (tid == 0) {
+    s_epoch = ld_volatile_u32(&B.control->scan_epoch);
+    s_tile = (int)atomicAdd(&B.control->scan_ticket, 1u);
+  }
+  __syncthreads();
+  const int tile = s_tile;
+  const uint32_t epoch = s_epoch;
+  const int64_t e = (int64_t)tile * kPreThreads + tid;
+  const bool live = e < P.num_envs;
+  const bool f_reset = live && B.reset[e] != 0;
+  const bool f_goal = live && B.goal_reset[e] != 0;
+
+  // ---- block scan + aggregate publication ---------------------------------------------------
+  __shared__ uint32_t s_wa[kPreThreads / 32], s_wb[kPreThreads / 32];
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned ba = __ballot_sync(0xffffffffu, f_reset), bb = __ballot_sync(0xffffffffu, f_goal);
+  if (lane == 0) { s_wa[warp] = __popc(ba); s_wb[warp] = __popc(bb); }
+  __syncthreads();
+  TileScan t;
+  t.tile = tile; t.epoch = epoch;
+  {
+    uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
+#pragma unroll
+    for (int w = 0; w < kPreThreads / 32; ++w) {
+      if (w < warp) { pa += s_wa[w]; pb += s_wb[w]; }
+      ta += s_wa[w]; tb += s_wb[w];
+    }
+    const unsigned below = (1u << lane) - 1u;
+    t.rank_a = pa + __popc(ba & below);
+    t.rank_b = pb + __popc(bb & below);
+    t.total_a = ta; t.total_b = tb;
+  }
+  if (tid == 0) {
+    const uint64_t st = tile == 0 ? kStateInclusive : kStateAggregate;
+    atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
+               (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
+  }
+
+  const uint64_t rng_epoch = B.control->rng_epoch;
+  uint32_t ex_a = 0, ex_b = 0;
+  const bool need_rank_first = P.inject_draws != 0;  // injected draws are indexed by compaction rank
+  if (need_rank_first) tile_scan_finish(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
+
+  // ---- action store (envs/env_base.py:369; clamp of wrappers/vec_task.py:162) -------------------
+  float act[LG_MAX_ACTION_DIM];
+  if (live) {
+    const int A = P.action_dim;
+    for (int c = 0; c < A; ++c) {
+      float a = action_in[e * A + c];
+      if (P.clip_input_actions) a = fminf(fmaxf(a, -P.clip_actions), P.clip_actions);
+      act[c] = f_reset ? 0.0f : a;  // reset zeroes the row after the store (trifinger_env.py:387)
+      B.action[e * A + c] = act[c];
+    }
+  }
+  // ---- resets (trifinger_env.py:373-440); goal reset second, as in env_base.py:374-379 ----------
+  if (f_reset) {
+    const DrawSource dr = make_draws(P, rng_epoch, e, kPurposeReset, B.inject_reset_u, B.inject_reset_n,
+                                     (int64_t)ex_a + t.rank_a);
+    reset_one_env(P, S, B, e, dr);
+  }
+  if (f_goal) {
+    const DrawSource dr = make_draws(P, rng_epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
+                                     (int64_t)ex_b + t.rank_b);
+    B.goal_reset[e] = 0;  // trifinger_env.py:427
+    apply_goal_sample(P, S, B, e, dr);
+  }
+  // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
+  if (live && B.applied_torque) torque_one_env(P, act, S.dof_state + e * 18, B.applied_torque + e * 9);
+
+  // ---- ordered id lists (env_base.py:374-379; trifinger_env.py:413-416, :435-436) ---------------
+  if (!need_rank_first) tile_scan_finish(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
+  if (f_reset) {
+    const int64_t j = (int64_t)ex_a + t.rank_a;
+    const int32_t base = (int32_t)(P.actors_per_env * e);
+    B.reset_ids[j] = e;
+    if (B.robot_indices) B.robot_indices[j] = base + P.robot_slot;
+    if (B.reset_root_indices) {  // unique(cat(robot, object, goal)) == sorted, and sorted == per-env triples
+      B.reset_root_indices[3 * j] = base + P.robot_slot;
+      B.reset_root_indices[3 * j + 1] = base + P.object_slot;
+      B.reset_root_indices[3 * j + 2] = base + P.goal_slot;
+    }
+  }
+  if (f_goal) {
+    const int64_t j = (int64_t)ex_b + t.rank_b;
+    B.goal_reset_ids[j] = e;
+    if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
+  }
+  if (tile == 0 && tid == 0 && P.use_device_clock) B.control->frame_count += P.control_decimation;
+}
+
+// standalone compaction (torch.nonzero(mask).view(-1))
+__global__ void __launch_bounds__(kPreThreads)
+compact_kernel(const uint8_t* __restrict__ mask, int64_t n, int64_t* __restrict__ ids, int32_t* counts2,
+               uint64_t* status, LgControl* ctl, int num_tiles) {
+  __shared__ int s_tile;
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    s_epoch = ld_volatile_u32(&ctl->scan_epoch);
+    s_tile = (int)atomicAdd(&ctl->scan_ticket, 1u);
+  }
+  __syncthreads();
+  const int64_t e = (int64_t)s_tile * kPreThreads + threadIdx.x;
+  const bool f = e < n && mask[e] != 0;
+  __shared__ uint32_t s_w[kPreThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned b = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) s_w[warp] = __popc(b);
+  __syncthreads();
+  TileScan t;
+  t.tile = s_tile; t.epoch = s_epoch;
+  uint32_t p = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kPreThreads / 32; ++w) { if (w < warp) p += s_w[w]; tot += s_w[w]; }
+  t.rank_a = p + __popc(b & ((1u << lane) - 1u));
+  t.rank_b = 0; t.total_a = tot; t.total_b = 0;
+  if (threadIdx.x == 0)
+    atomicExch(reinterpret_cast<unsigned long long*>(status + t.tile),
+               (unsigned long long)pack_status(t.epoch, t.tile == 0 ? kStateInclusive : kStateAggregate, tot, 0));
+  uint32_t ex_a, ex_b;
+  tile_scan_finish(ctl, status, t, num_tiles, ex_a, ex_b, counts2);
+  if (f) ids[(int64_t)ex_a + t.rank_a] = e;
+}
+
+// hooks on explicit id lists
+__global__ void reset_ids_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B,
+                                 const int64_t* __restrict__ ids, int64_t k, int goal_only) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < k) {
+    const int64_t e = ids[j];
+    const uint64_t epoch = B.control->rng_epoch;
+    if (goal_only) {
+      const DrawSource dr = make_draws(P, epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n, j);
+      B.goal_reset[e] = 0;
+      apply_goal_sample(P, S, B, e, dr);
+      if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
+    } else {
+      const DrawSource dr = make_draws(P, epoch, e, kPurposeReset, B.inject_reset_u, B.inject_reset_n, j);
+      reset_one_env(P, S, B, e, dr);
+      const int32_t base = (int32_t)(P.actors_per_env * e);
+      if (B.robot_indices) B.robot_indices[j] = base + P.robot_slot;
+      if (B.reset_root_indices) {
+        B.reset_root_indices[3 * j] = base + P.robot_slot;
+        B.reset_root_indices[3 * j + 1] = base + P.object_slot;
+        B.reset_root_indices[3 * j + 2] = base + P.goal_slot;
+      }
+    }
+  }
+}
+__global__ void bump_epoch_kernel(LgControl* ctl) { ctl->rng_epoch += 1; }
+
+__global__ void pre_step_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.num_envs) return;
+  float act[LG_MAX_ACTION_DIM];
+  for (int c = 0; c < P.action_dim; ++c) act[c] = B.action[e * P.action_dim + c];
+  torque_one_env(P, act, S.dof_state + e * 18, B.applied_torque + e * 9);
+}
+
+// ---- batched primitives -------------------------------------------------------------------------
+__global__ void quat_mul_kernel(const float* a, const float* b, float* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 qa = reinterpret_cast<const float4*>(a)[i], qb = reinterpret_cast<const float4*>(b)[i];
+  const Quat r = quat_mul(Quat{qa.x, qa.y, qa.z, qa.w}, Quat{qb.x, qb.y, qb.z, qb.w});
+  reinterpret_cast<float4*>(out)[i] = make_float4(r.x, r.y, r.z, r.w);
+}
+__global__ void quat_diff_kernel(const float* a, const float* b, float* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 qa = reinterpret_cast<const float4*>(a)[i], qb = reinterpret_cast<const float4*>(b)[i];
+  out[i] = quat_diff_rad(Quat{qa.x, qa.y, qa.z, qa.w}, Quat{qb.x, qb.y, qb.z, qb.w});
+}
+template <int OP>
+__global__ void rowwise_kernel(const float* x, const float* lo, const float* hi, float* out, int64_t total, int dims) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % dims);
+  const float l = lo[c], h = hi[c], v = x[i];
+  if (OP == 0) out[i] = scale_transform(v, (l + h) * 0.5f, h - l);
+  else if (OP == 1) out[i] = unscale_transform(v, l, h);
+  else out[i] = saturate(v, l, h);
+}
+__global__ void lgsk_kernel(const float* x, float scale, float* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = lgsk(x[i], scale);
+}
+// extension: the 8 cube corners (+-s/2)^3 rotated by the pose quaternion and translated
+__device__ __forceinline__ void quat_rotate(const Quat q, float vx, float vy, float vz, float& ox, float& oy, float& oz) {
+  // v' = v + 2 w (q_v x v) + 2 q_v x (q_v x v)
+  const float tx = 2.0f * (q.y * vz - q.z * vy), ty = 2.0f * (q.z * vx - q.x * vz), tz = 2.0f * (q.x * vy - q.y * vx);
+  ox = vx + q.w * tx + (q.y * tz - q.z * ty);
+  oy = vy + q.w * ty + (q.z * tx - q.x * tz);
+  oz = vz + q.w * tz + (q.x * ty - q.y * tx);
+}
+__global__ void keypoints_kernel(const float* pose, float size, float* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 8) return;
+  const int64_t e = i >> 3;
+  const int k = (int)(i & 7);
+  const float* p = pose + e * 7;
+  const float h = size * 0.5f;
+  const float vx = (k & 1) ? h : -h, vy = (k & 2) ? h : -h, vz = (k & 4) ? h : -h;
+  float rx, ry, rz;
+  quat_rotate(Quat{p[3], p[4], p[5], p[6]}, vx, vy, vz, rx, ry, rz);
+  out[i * 3] = p[0] + rx; out[i * 3 + 1] = p[1] + ry; out[i * 3 + 2] = p[2] + rz;
+}
+
+}  // namespace lg
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+namespace {
+thread_local std::string g_error;
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+int check_launch(const char* what) {
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+  return LG_OK;
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int validate(const LgParams* P, const LgSimState* S, const LgBuffers* B, bool need_states) {
+  if (!P || !S || !B) return fail(LG_ERR_BAD_ARG, "null LgParams / LgSimState / LgBuffers");
+  if (P->num_envs <= 0) return fail(LG_ERR_BAD_ARG, "num_envs must be positive");
+  if (P->num_envs >= (1 << 23)) return fail(LG_ERR_BAD_ARG, "num_envs per shard must be < 2^23");
+  if (P->action_dim != 9 && P->action_dim != 18) return fail(LG_ERR_BAD_ARG, "action_dim must be 9 or 18");
+  if (!S->dof_state || !S->root_state || !S->rigid_body) return fail(LG_ERR_BAD_ARG, "null simulator tensor");
+  if (!B->obs || !B->action || !B->reward || !B->reset || !B->goal_reset || !B->successes || !B->steps_count ||
+      !B->goal_pose || !B->goal_movement || !B->history || !B->control)
+    return fail(LG_ERR_BAD_ARG, "null env buffer");
+  if (need_states && P->asymmetric_obs && (!B->states || !S->dof_force || !S->ft_sensors))
+    return fail(LG_ERR_BAD_ARG, "asymmetric_obs needs states, dof_force and ft_sensors");
+  const void* al[] = {S->dof_state, S->dof_force, S->ft_sensors, B->obs, B->states, B->obs_clipped, B->states_clipped,
+                      B->action, B->goal_pose, B->history};
+  for (const void* p : al)
+    if (p && !aligned16(p)) return fail(LG_ERR_BAD_ARG, "tensor base pointers must be 16-byte aligned");
+  return LG_OK;
+}
+
+template <bool REWARD>
+int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, double sched, cudaStream_t st) {
+  if (int rc = validate(P, S, B, true)) return rc;
+  if (REWARD && (!B->stats_accum || !B->stats || !B->step_info))
+    return fail(LG_ERR_BAD_ARG, "null statistics buffer");
+  const int grid = (int)((P->num_envs + lg::kTileEnvs - 1) / lg::kTileEnvs);
+  const bool asym = P->asymmetric_obs != 0;
+#define LG_LAUNCH(AD, AS) lg::post_physics_kernel<AD, AS, REWARD><<<grid, lg::kPostThreads, 0, st>>>(*P, *S, *B, sched)
+  if (P->action_dim == 9) { if (asym) LG_LAUNCH(9, true); else LG_LAUNCH(9, false); }
+  else { if (asym) LG_LAUNCH(18, true); else LG_LAUNCH(18, false); }
+#undef LG_LAUNCH
+  return check_launch("post_physics_kernel");
+}
+}  // namespace
+
+extern "C" {
+
+int lg_version(void) { return LG_VERSION; }
+const char* lg_last_error(void) { return g_error.c_str(); }
+size_t lg_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(LgParams);
+    case 1: return sizeof(LgSimState);
+    case 2: return sizeof(LgBuffers);
+    case 3: return sizeof(LgControl);
+    case 4: return sizeof(LgRewardTerm);
+    case 5: return sizeof(LgHostStep);
+    default: return 0;
+  }
+}
+int64_t lg_scan_tiles(int64_t n) { return (n + lg::kPreThreads - 1) / lg::kPreThreads; }
+
+int lg_post_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, double sched_step, void* stream) {
+  return launch_post<true>(P, S, B, sched_step, (cudaStream_t)stream);
+}
+int lg_fill_observations(const LgParams* P, const LgSimState* S, const LgBuffers* B, void* stream) {
+  return launch_post<false>(P, S, B, 0.0, (cudaStream_t)stream);
+}
+int lg_init_history(const LgParams* P, const LgSimState* S, const LgBuffers* B, void* stream) {
+  if (int rc = validate(P, S, B, false)) return rc;
+  const int64_t total = P->num_envs * LG_HISTORY_COLS;
+  lg::init_history_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*P, *S, *B);
+  return check_launch("init_history_kernel");
+}
+
+int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in, void* stream) {
+  if (int rc = validate(P, S, B, false)) return rc;
+  if (!action_in) return fail(LG_ERR_BAD_ARG, "null action_in");
+  if (!B->scan_status || !B->reset_ids || !B->goal_reset_ids || !B->counts)
+    return fail(LG_ERR_BAD_ARG, "null compaction buffer");
+  if (P->inject_draws && !(B->inject_reset_u || B->inject_goal_u || B->inject_reset_n || B->inject_goal_n))
+    return fail(LG_ERR_BAD_ARG, "inject_draws set without injected arrays");
+  const int tiles = (int)lg_scan_tiles(P->num_envs);
+  lg::pre_physics_kernel<<<tiles, lg::kPreThreads, 0, (cudaStream_t)stream>>>(*P, *S, *B, action_in, tiles);
+  return check_launch("pre_physics_kernel");
+}
+
+int lg_compact(const uint8_t* mask, int64_t n, int64_t* ids_out, int32_t* count_out, uint64_t* status,
+               LgControl* control, void* stream) {
+  if (!mask || !ids_out || !count_out || !status || !control) return fail(LG_ERR_BAD_ARG, "null argument");
+  if (n < 0 || n >= (1 << 23)) return fail(LG_ERR_BAD_ARG, "n out of range");
+  if (n == 0) { cudaMemsetAsync(count_out, 0, 2 * sizeof(int32_t), (cudaStream_t)stream); return check_launch("memset"); }
+  const int tiles = (int)lg_scan_tiles(n);
+  lg::compact_kernel<<<tiles, lg::kPreThreads, 0, (cudaStream_t)stream>>>(mask, n, ids_out, count_out, status, control, tiles);
+  return check_launch("compact_kernel");
+}
+
+static int reset_list(const LgParams* P, const LgSimState* S, const LgBuffers* B, const int64_t* ids, int64_t k,
+                      int goal_only, void* stream) {
+  if (int rc = validate(P, S, B, false)) return rc;
+  if (k < 0 || (k > 0 && !ids)) return fail(LG_ERR_BAD_ARG, "bad id list");
+  if (k == 0) return LG_OK;
+  lg::reset_ids_kernel<<<(unsigned)((k + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, *S, *B, ids, k, goal_only);
+  if (int rc = check_launch("reset_ids_kernel")) return rc;
+  lg::bump_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(B->control);
+  return check_launch("bump_epoch_kernel");
+}
+int lg_reset_envs(const LgParams* P, const LgSimState* S, const LgBuffers* B, const int64_t* ids, int64_t k, void* stream) {
+  return reset_list(P, S, B, ids, k, 0, stream);
+}
+int lg_goal_reset_envs(const LgParams* P, const LgSimState* S, const LgBuffers* B, const int64_t* ids, int64_t k, void* stream) {
+  return reset_list(P, S, B, ids, k, 1, stream);
+}
+
+int lg_pre_step(const LgParams* P, const LgSimState* S, const LgBuffers* B, void* stream) {
+  if (int rc = validate(P, S, B, false)) return rc;
+  if (!B->applied_torque) return fail(LG_ERR_BAD_ARG, "null applied_torque");
+  lg::pre_step_kernel<<<(unsigned)((P->num_envs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*P, *S, *B);
+  return check_launch("pre_step_kernel");
+}
+
+#define LG_GRID(n) (unsigned)(((n) + 255) / 256), 256, 0, (cudaStream_t)stream
+int lg_quat_mul(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  if (!aligned16(a) || !aligned16(b) || !aligned16(out)) return fail(LG_ERR_BAD_ARG, "quaternion arrays must be 16-byte aligned");
+  if (n) lg::quat_mul_kernel<<<LG_GRID(n)>>>(a, b, out, n);
+  return check_launch("quat_mul_kernel");
+}
+int lg_quat_diff_rad(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  if (!aligned16(a) || !aligned16(b)) return fail(LG_ERR_BAD_ARG, "quaternion arrays must be 16-byte aligned");
+  if (n) lg::quat_diff_kernel<<<LG_GRID(n)>>>(a, b, out, n);
+  return check_launch("quat_diff_kernel");
+}
+static int rowwise(int op, const float* x, const float* lo, const float* hi, float* out, int64_t n, int32_t dims, void* stream) {
+  if (!x || !lo || !hi || !out || n < 0 || dims <= 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  const int64_t total = n * dims;
+  if (total == 0) return LG_OK;
+  if (op == 0) lg::rowwise_kernel<0><<<LG_GRID(total)>>>(x, lo, hi, out, total, dims);
+  else if (op == 1) lg::rowwise_kernel<1><<<LG_GRID(total)>>>(x, lo, hi, out, total, dims);
+  else lg::rowwise_kernel<2><<<LG_GRID(total)>>>(x, lo, hi, out, total, dims);
+  return check_launch("rowwise_kernel");
+}
+int lg_scale_transform(const float* x, const float* lo, const float* hi, float* out, int64_t n, int32_t d, void* s) { return rowwise(0, x, lo, hi, out, n, d, s); }
+int lg_unscale_transform(const float* x, const float* lo, const float* hi, float* out, int64_t n, int32_t d, void* s) { return rowwise(1, x, lo, hi, out, n, d, s); }
+int lg_saturate(const float* x, const float* lo, const float* hi, float* out, int64_t n, int32_t d, void* s) { return rowwise(2, x, lo, hi, out, n, d, s); }
+int lg_lgsk_kernel(const float* x, float scale, float* out, int64_t n, void* stream) {
+  if (!x || !out || n < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  if (n) lg::lgsk_kernel<<<LG_GRID(n)>>>(x, scale, out, n);
+  return check_launch("lgsk_kernel");
+}
+int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n, void* stream) {
+  if (!pose || !out || n < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  if (n) lg::keypoints_kernel<<<LG_GRID(n * 8)>>>(pose, cube_size, out, n);
+  return check_launch("keypoints_kernel");
+}
+
+int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {
+  if (int rc = validate(P, S, B, true)) return rc;
+  if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||
+      !H->obs_host || !H->reward_host)
+    return fail(LG_ERR_BAD_ARG, "null host buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = P->num_envs;
+  const int obs_dim = 32 + P->action_dim, state_dim = obs_dim + 72;
+  // the action arrives first: the pre-physics pass (resets, torque) consumes it together with last step's state
+  cudaMemcpyAsync(H->action_staging, H->action_host, sizeof(float) * N * P->action_dim, cudaMemcpyHostToDevice, st);
+  if (int rc = lg_pre_physics(P, S, B, H->action_staging, stream)) return rc;
+  // "physics": the simulator's new state lands in the device tensors
+  cudaMemcpyAsync(S->dof_state, H->dof_state_host, sizeof(float) * N * 18, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(S->root_state, H->root_state_host, sizeof(float) * N * P->actors_per_env * 13, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(const_cast<float*>(S->rigid_body), H->rigid_body_host, sizeof(float) * N * P->bodies_per_env * 13, cudaMemcpyHostToDevice, st);
+  if (P->asymmetric_obs) {
+    if (!H->dof_force_host || !H->ft_sensors_host || !H->states_host) return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
+    cudaMemcpyAsync(const_cast<float*>(S->dof_force), H->dof_force_host, sizeof(float) * N * 9, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(const_cast<float*>(S->ft_sensors), H->ft_sensors_host, sizeof(float) * N * 18, cudaMemcpyHostToDevice, st);
+  }
+  if (int rc = lg_post_physics(P, S, B, sched_step, stream)) return rc;
+  const float* obs_src = B->obs_clipped ? B->obs_clipped : B->obs;
+  cudaMemcpyAsync(H->obs_host, obs_src, sizeof(float) * N * obs_dim, cudaMemcpyDeviceToHost, st);
+  if (P->asymmetric_obs) {
+    const float* st_src = B->states_clipped ? B->states_clipped : B->states;
+    cudaMemcpyAsync(H->states_host, st_src, sizeof(float) * N * state_dim, cudaMemcpyDeviceToHost, st);
+  }
+  cudaMemcpyAsync(H->reward_host, B->reward, sizeof(float) * N, cudaMemcpyDeviceToHost, st);
+  if (H->dones_host && B->dones) cudaMemcpyAsync(H->dones_host, B->dones, N, cudaMemcpyDeviceToHost, st);
+  return check_launch("lg_step_host");
+}
+
+}  // extern "C"

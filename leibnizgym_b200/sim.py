@@ -1,0 +1,71 @@
+"""Synthetic stand-in for the IsaacGym tensor API.
+
+PhysX is out of scope; what the hot path needs from the simulator is (a) the five
+state tensors it reads zero-copy (ref envs/trifinger/trifinger_env.py:592-617),
+(b) a frame counter (ref envs/env_base.py:286-289) and (c) somewhere for the
+reset rows to go.  `SyntheticSim` owns those tensors on the GPU and "steps" by
+copying the next state of a `StateSequence` into them in place, exactly what the
+reference harness' FakeGym does on the CPU (tests/golden/ref_harness.py).
+
+The sequence may live on the device (device-to-device copy) or in pinned host
+memory (host-to-device copy: the situation of the reference's default
+`use_gpu_pipeline: False`, where the simulator state is host-resident).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .synthetic import StateSequence
+
+
+class SyntheticSim:
+    def __init__(self, seq: StateSequence, device: str = "cuda:0"):
+        self.seq = seq
+        self.device = torch.device(device)
+        self.num_envs = seq.num_envs
+        N = self.num_envs
+        f32 = dict(device=self.device, dtype=torch.float32)
+        self.dof_state = torch.zeros(N, 9, 2, **f32)
+        self.root_state = torch.zeros(4 * N, 13, **f32)
+        self.rigid_body = torch.zeros(N, 20, 13, **f32)
+        self.dof_force = torch.zeros(N, 9, **f32)
+        self.ft_sensors = torch.zeros(N, 18, **f32)
+        self.frame_count = 0
+        self.cursor = 0
+        self.fingertip_bodies = (6, 11, 16)
+        self.bodies_per_env, self.actors_per_env = 20, 4
+        self.slots = (0, 2, 3)  # robot, object, goal actor slots inside one env
+        self.before_simulate: Optional[Callable[["SyntheticSim"], None]] = None  # test hook
+        self.applied_torque = None
+        self._load(0)  # what refresh_* shows before the first simulate
+
+    def _load(self, t: int) -> None:
+        s = self.seq
+        nb = s.dof_state.device.type == "cpu"
+        self.dof_state.copy_(s.dof_state[t], non_blocking=nb)
+        self.root_state.copy_(s.root_state[t], non_blocking=nb)
+        self.rigid_body.copy_(s.rigid_body[t], non_blocking=nb)
+        self.dof_force.copy_(s.dof_force[t], non_blocking=nb)
+        self.ft_sensors.copy_(s.ft_sensors[t], non_blocking=nb)
+
+    # -- the slice of the gym API the path uses ---------------------------------------
+    def simulate(self) -> None:
+        if self.before_simulate is not None:
+            self.before_simulate(self)
+        self._load(self.cursor % self.seq.num_steps)
+        self.cursor += 1
+        self.frame_count += 1
+
+    def get_frame_count(self) -> int:
+        return self.frame_count
+
+    def set_dof_actuation_force_tensor(self, torque: torch.Tensor) -> None:
+        self.applied_torque = torque
+
+    def set_dof_state_tensor_indexed(self, indices: torch.Tensor, count) -> None:
+        """Reset rows are already in `dof_state` (simulator memory); a real backend is notified here."""
+
+    def set_actor_root_state_tensor_indexed(self, indices: torch.Tensor, count) -> None:
+        """As above for `root_state`."""

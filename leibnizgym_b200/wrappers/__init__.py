@@ -1,0 +1,3 @@
+from .vec_task import VecTask, VecTaskPython
+
+__all__ = ["VecTask", "VecTaskPython"]
