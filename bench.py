@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the TriFinger MDP hot path (reward + obs/states + reset), BASELINE.json metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+
+A "step" is one pass of the hot path over all envs of the workload: lg_pre_physics (action store,
+ordered reset compaction, reset / goal sampling, action->torque) + lg_post_physics (obs, states,
+six reward terms, termination, counters, episode statistics).  PhysX is replaced by a ring of
+synthetic simulator states resident in HBM (leibnizgym_b200/synthetic.py).
+
+One JSON line is printed by rank 0:
+  value      env-steps/s over all GPUs, inputs resident in HBM, K steps replayed from CUDA graphs,
+             timed with CUDA events, max over ranks
+  e2e        the same metric through the public API (VecTaskPython.step + get_state) with the
+             simulator state and the action in pinned HOST memory and obs/states/reward/dones
+             read back to the host every step
+  roofline   dominant kernel (post_physics) alone: algorithmic bytes / measured launch duration
+             against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's torch CPU path on the host cores (N = 1 only)
+`--impl reference` times that CPU path alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from leibnizgym_b200.config import difficulty_config, resolve_config  # noqa: E402
+from leibnizgym_b200.synthetic import bernoulli_masks, make_sequence  # noqa: E402
+
+METRIC = "env-steps/sec reward+obs+reset"
+UNIT = "env-steps/s"
+FALLBACK_HBM_GBS = 6650.0
+
+# BASELINE.json configs -> concrete runs.  envs are PER GPU (weak scaling).
+WORKLOADS = {
+    "c2": dict(desc="trifinger_difficulty_2, asymmetric obs+states, 16384 envs/GPU", difficulty=2, envs=16384,
+               asym=True, seed=1002, reset_p=0.0),
+    "c3": dict(desc="trifinger_difficulty_3, asymmetric, 65536 envs/GPU, 5% forced resets/step", difficulty=3,
+               envs=65536, asym=True, seed=1003, reset_p=0.05),
+    "c4": dict(desc="trifinger_difficulty_4, asymmetric obs+states, 32768 envs/GPU (262144 over 8)", difficulty=4,
+               envs=32768, asym=True, seed=1004, reset_p=0.0),
+    "c5": dict(desc="reset-heavy: difficulty 4, asymmetric, 16384 envs/GPU, 30% envs reset per step", difficulty=4,
+               envs=16384, asym=True, seed=1005, reset_p=0.3),
+    "c2sym": dict(desc="trifinger_difficulty_2, symmetric obs only, 16384 envs/GPU", difficulty=2, envs=16384,
+                  asym=False, seed=1002, reset_p=0.0),
+}
+
+# algorithmic bytes per env-step (derivation in DESIGN.md §5)
+POST_BYTES = {True: 526 + 695, False: 298 + 243}
+PRE_BYTES = 2 + 36 + 36 + 72 + 36          # flags, action in, action out, dof_state (safety damping), torque out
+RESET_BYTES = 300                           # extra per resetting env
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled every few ms while the GPU is under load (NVML)."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        self.enabled = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.enabled = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.enabled:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) — cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def time_cpu_path(wl: dict, envs: int, steps: int, warmup: int, max_seconds: float):
+    """Times the hot path only (simulator playback excluded) of the oracle port on host cores."""
+    from oracle.trifinger_oracle import OracleEnv, OracleSim
+
+    class TimedSim(OracleSim):
+        sim_seconds = 0.0
+
+        def simulate(self):
+            t0 = time.perf_counter()
+            super().simulate()
+            TimedSim.sim_seconds += time.perf_counter() - t0
+
+    cfg = resolve_config(difficulty_config(wl["difficulty"], envs, asymmetric_obs=wl["asym"], seed=wl["seed"]))
+    T = 4
+    seq = make_sequence(wl["seed"], T, envs)
+    masks = bernoulli_masks(wl["seed"], T, envs, wl["reset_p"])
+    env = OracleEnv(cfg, TimedSim(seq, envs))
+    env.reset()
+    for t in range(warmup):
+        env.step(seq.action[t % T])
+    done = 0
+    TimedSim.sim_seconds = 0.0
+    t0 = time.perf_counter()
+    while done < steps:
+        if masks is not None:
+            env.reset_buf |= masks[done % T]
+        env.step(seq.action[done % T])
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    wall = time.perf_counter() - t0
+    hot = wall - TimedSim.sim_seconds
+    return dict(env_steps_per_s=done * envs / hot, ms_per_step=1e3 * hot / done, steps=done, envs=envs,
+                cores=torch.get_num_threads())
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: each step covers a slice of the workload's envs so K steps end within ~1 min
+    budget_env_steps = 4.0e7
+    envs = int(min(wl["envs"], max(256, 2 ** int(math.log2(max(budget_env_steps / max(args.steps, 1), 256))))))
+    r = time_cpu_path(wl, envs, args.steps, max(args.warmup, 3) if args.warmup < 16 else 16, max_seconds=150.0)
+    sample = (f"{r['steps']} steps x {envs} envs of the workload's {wl['envs']} per step, oracle port of the reference's "
+              f"torch CPU path, {r['cores']} torch threads, simulator playback excluded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["env_steps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "envs_per_step_sampled": envs},
+        "cpu_baseline": {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["env_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, wl):
+    import torch.distributed as dist
+
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.graph_runner import GraphRunner
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.wrappers import VecTaskPython
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    N = wl["envs"]
+    K, W = args.steps, max(args.warmup, 3)
+    R = args.ring
+    asym = wl["asym"]
+
+    cfg = difficulty_config(wl["difficulty"], N * world, asymmetric_obs=asym, seed=wl["seed"])
+    ring = make_sequence(wl["seed"], R, N, device=dev, first_env=rank * N)
+    masks = bernoulli_masks(wl["seed"] + rank, R, N, wl["reset_p"], device=dev)
+    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(ring, dev), rank=rank, world_size=world)
+    env.reset()
+    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks)
+
+    stream = torch.cuda.Stream()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream), sampler:
+        C = R * max(1, 128 // R)          # steps per graph: whole ring, ~128 steps
+        q, rem = divmod(K, C)
+        runner.capture(C)
+        main_graph = runner.graph
+        tail_graph = None
+        if rem:
+            runner.capture(rem)
+            tail_graph = runner.graph
+        # ---- warm-up ---------------------------------------------------------------------------
+        for _ in range(max(1, math.ceil(W / C))):
+            main_graph.replay()
+        barrier()
+        # ---- timed region: exactly K steps -----------------------------------------------------
+        e0, e1 = ev(), ev()
+        e0.record()
+        for i in range(q):
+            main_graph.replay()
+            if world > 1 and (i % 4) == 3:   # episode statistics: the path's only collective
+                dist.all_reduce(env._step_stats.clone(), op=dist.ReduceOp.SUM)
+        if tail_graph is not None:
+            tail_graph.replay()
+        e1.record()
+        barrier()
+        step_ms_total = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([step_ms_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            step_ms_total = float(t.item())
+        # ---- dominant kernel alone (post_physics), same ring, same launch count -------------------
+        runner.capture(C, post_only=True)
+        post_graph = runner.graph
+        post_graph.replay()
+        torch.cuda.synchronize()
+        p0, p1 = ev(), ev()
+        reps = max(1, K // C)
+        p0.record()
+        for _ in range(reps):
+            post_graph.replay()
+        p1.record()
+        torch.cuda.synchronize()
+        post_us = 1e3 * p0.elapsed_time(p1) / (reps * C)
+
+    # ---- end to end through the public API with host buffers (rank-local, then max over ranks) ----
+    e2e = run_e2e(args, wl, cfg, dev, rank, world)
+    clocks = sampler.summary()
+
+    total_env_steps = float(K) * N * world
+    value = total_env_steps / (step_ms_total * 1e-3)
+    peak, peak_src = hbm_peak()
+    post_bytes = POST_BYTES[asym] * N
+    achieved = post_bytes / (post_us * 1e-6) / 1e9
+    step_bytes = (POST_BYTES[asym] + PRE_BYTES + wl["reset_p"] * RESET_BYTES) * N
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"dp{world}",
+                   "l2_policy": f"inputs larger than L2: ring of {R} distinct simulator states "
+                                f"({ring.nbytes() / 2**20:.0f} MiB) and {R} output slots per GPU",
+                   "steps_per_graph": C, "reset_fraction_per_step": wl["reset_p"]},
+        "roofline": {"bound": "hbm", "kernel": "post_physics_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,
+                     "whole_step_gbs": step_bytes / (step_ms_total / K * 1e-3) / 1e9},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": 2 * K,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = time_cpu_path(wl, N, steps=10_000, warmup=3, max_seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {
+            "value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"{r['steps']} steps x {N} envs (~{args.cpu_seconds:.0f} s), oracle port of the reference's torch CPU "
+                      f"path, simulator playback excluded"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, cfg, dev, rank, world):
+    """Public-API step with HOST-resident simulator state: every step uploads the five simulator
+    tensors + the action from pinned memory and downloads obs, states, reward, dones."""
+    import torch.distributed as dist
+
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.wrappers import VecTaskPython
+
+    N = wl["envs"]
+    T = 4
+    host = make_sequence(wl["seed"], T, N, first_env=rank * N).to("cpu", pin=True)
+    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(host, dev), rank=rank, world_size=world)
+    vec = VecTaskPython(env, rl_device=dev, clip_obs=5.0, clip_actions=1.0)
+    vec.reset()
+    asym = wl["asym"]
+    pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()  # noqa: E731
+    h_obs, h_rew, h_done = pin(N, env.get_obs_dim()), pin(N), pin(N, dt=torch.bool)
+    h_states = pin(N, env.get_state_dim()) if asym else None
+    steps = max(8, min(args.e2e_steps, args.steps))
+
+    def one(t):
+        obs, rew, done, _ = vec.step(host.action[t % T])   # host action -> device inside step()
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        if asym:
+            h_states.copy_(vec.get_state(), non_blocking=True)
+        torch.cuda.synchronize()                           # the caller consumes the results every step
+
+    for t in range(3):
+        one(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        one(t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    h2d = 4 * N * (18 + 4 * 13 + 20 * 13 + 9 + 18 + 9)
+    d2h = 4 * N * (env.get_obs_dim() + env.get_state_dim() + 1) + N
+    return {"value": steps * N * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": steps, "ms_per_step": ms / steps,
+            "api": "VecTaskPython.step + get_state, pinned host simulator state"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20480)
+    ap.add_argument("--warmup", type=int, default=512)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="override envs per GPU")
+    ap.add_argument("--ring", type=int, default=32, help="distinct simulator states in HBM")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl["envs"] = args.envs
+        wl["desc"] += f" [envs/GPU overridden to {args.envs}]"
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,7 @@ typedef struct LgParams {
    * the observation table (trifinger_env.py:663-710) */
   float scale_centre[LG_MAX_STATE_DIM];
   float scale_span[LG_MAX_STATE_DIM];
+  float scale_rcp[LG_MAX_STATE_DIM];   /* fp32(1/span), correctly rounded: lets the kernel divide in 3 instructions */
   /* pre_step tables (trifinger_env.py:442-498) */
   float action_low[LG_MAX_ACTION_DIM], action_high[LG_MAX_ACTION_DIM];
   float kp[9], kd[9], safety_kd[9];
@@ -138,12 +139,12 @@ typedef struct LgParams {
 
 /* Device-resident control block (one per env shard; zero-initialised by the caller). */
 typedef struct LgControl {
-  uint64_t rng_epoch;     /* advanced once per lg_pre_physics / lg_reset_envs / lg_goal_reset_envs */
+  uint64_t rng_epoch;     /* RNG epoch of lg_reset_envs / lg_goal_reset_envs, advanced once per call       */
   int64_t frame_count;    /* simulator frames; advanced by lg_pre_physics when P.use_device_clock  */
   uint32_t scan_ticket;   /* tile ticket dispenser of the ordered compaction                        */
-  uint32_t scan_epoch;    /* validity tag of the look-back status words                             */
-  uint32_t post_done;     /* CTA completion counter of lg_post_physics                              */
-  uint32_t _pad;
+  uint32_t scan_epoch;    /* validity tag of the look-back status words; advances once per compaction
+                             launch and doubles as the RNG epoch of the fused resets                */
+  uint32_t _pad[2];
 } LgControl;
 
 /* The simulator-owned tensors (zero-copy views in the reference, trifinger_env.py:602-617). */
@@ -174,10 +175,9 @@ typedef struct LgBuffers {
                                only columns of history entry 1 the path reads  */
   float* applied_torque;    /* optional [N, 9]: what set_dof_actuation_force_tensor receives    */
   float* term_rewards;      /* optional [LG_NUM_TERMS, N]: every term's value (parity tests)    */
-  double* stats_accum;      /* [LG_NUM_STATS] running sums, must be zero before the first step  */
-  double* stats;            /* [LG_NUM_STATS] sums of the last completed post-physics pass      */
-  float* step_info;         /* [LG_NUM_STATS] the reference's `_step_info` values for this shard:
-                               means for the reward terms and successes, counts for the rest    */
+  double* step_stats;       /* [LG_NUM_STATS] this shard's `_step_info`: means of the reward terms, of the
+                               total reward and of `_successes`, counts for the rest.  Zeroed by
+                               lg_pre_physics, accumulated (fp64 RED) by lg_post_physics              */
   /* compaction outputs (env_base.py:374-379, trifinger_env.py:413-416, :435-436) */
   int64_t* reset_ids;       /* [N] ascending env ids with _reset_buf set                        */
   int64_t* goal_reset_ids;  /* [N] ascending env ids with _goal_reset_buf set                   */
@@ -257,6 +257,10 @@ int lg_unscale_transform(const float* x, const float* lower, const float* upper,
 int lg_saturate(const float* x, const float* lower, const float* upper, float* out,
                 int64_t n, int32_t dims, void* stream);                                     /* :60-75   */
 int lg_lgsk_kernel(const float* x, float scale, float* out, int64_t n, void* stream);       /* rewards.py:20-34 */
+
+/* Self-test: counts numerators x (all 2^32 bit patterns) for which the kernels' fast division by
+ * `span` (using `rcp` = fp32(1/span)) differs from IEEE x / span.  Expected result: 0. */
+int lg_selftest_division(float span, float rcp, unsigned long long* mismatches_dev, void* stream);
 
 /* Extension (no reference code): world-frame cube corners, [n,7] poses -> [n,8,3] keypoints. */
 int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n, void* stream);

@@ -49,6 +49,7 @@ class LgParams(C.Structure):
         ("goal_rate_magnitude", C.c_double),
         ("terms", LgRewardTerm * LG_NUM_TERMS),
         ("scale_centre", C.c_float * LG_MAX_STATE_DIM), ("scale_span", C.c_float * LG_MAX_STATE_DIM),
+        ("scale_rcp", C.c_float * LG_MAX_STATE_DIM),
         ("action_low", C.c_float * LG_MAX_ACTION_DIM), ("action_high", C.c_float * LG_MAX_ACTION_DIM),
         ("kp", C.c_float * 9), ("kd", C.c_float * 9), ("safety_kd", C.c_float * 9),
         ("torque_low", C.c_float * 9), ("torque_high", C.c_float * 9),
@@ -66,7 +67,7 @@ class LgParams(C.Structure):
 
 class LgControl(C.Structure):
     _fields_ = [("rng_epoch", C.c_uint64), ("frame_count", C.c_int64), ("scan_ticket", C.c_uint32),
-                ("scan_epoch", C.c_uint32), ("post_done", C.c_uint32), ("_pad", C.c_uint32)]
+                ("scan_epoch", C.c_uint32), ("_pad", C.c_uint32 * 2)]
 
 
 class LgSimState(C.Structure):
@@ -78,7 +79,7 @@ class LgBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "states", "obs_clipped", "states_clipped", "action", "reward", "reset", "goal_reset",
         "successes", "dones", "steps_count", "goal_pose", "goal_movement", "history", "applied_torque",
-        "term_rewards", "stats_accum", "stats", "step_info", "reset_ids", "goal_reset_ids", "counts",
+        "term_rewards", "step_stats", "reset_ids", "goal_reset_ids", "counts",
         "robot_indices", "reset_root_indices", "goal_root_indices", "scan_status", "control",
         "inject_reset_u", "inject_reset_n", "inject_goal_u", "inject_goal_n")]
 
@@ -112,6 +113,7 @@ SYMBOLS = {
     "lg_saturate": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "lg_lgsk_kernel": (C.c_int, [_vp, C.c_float, _vp, _i64, _vp]),
     "lg_cube_keypoints": (C.c_int, [_vp, C.c_float, _vp, _i64, _vp]),
+    "lg_selftest_division": (C.c_int, [C.c_float, C.c_float, _vp, _vp]),
     "lg_step_host": (C.c_int, [_P, _S, _B, C.POINTER(LgHostStep), C.c_double, _vp]),
 }
 

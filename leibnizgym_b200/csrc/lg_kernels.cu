@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -18,11 +19,11 @@
 namespace lg {
 
 // =========================================================================================
-// post-physics: one CTA = one tile of kTileEnvs envs, kSubs threads per env
+// post-physics: one CTA = one tile of E envs, 4 threads per env
 // =========================================================================================
-constexpr int kTileEnvs = 32;
 constexpr int kSubs = 4;
-constexpr int kPostThreads = kTileEnvs * kSubs;  // 128
+constexpr int kTileEnvs = 32;
+constexpr int kPostThreads = 256;
 
 template <int A, bool ASYM>
 struct Layout {
@@ -49,51 +50,123 @@ __device__ __forceinline__ double sched_ramp(const LgRewardTerm& t, double T) { 
   return 1.0;
 }
 
-// cooperative tile load: 128-bit streaming loads over the contiguous slab, scalar tail
-template <typename Sink>
-__device__ __forceinline__ void slab_load(const float* __restrict__ src, int nfloats, Sink&& sink) {
-  const int n4 = nfloats >> 2;
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
-    const float4 v = ld_stream4(s4 + j);
-    sink(4 * j, v.x); sink(4 * j + 1, v.y); sink(4 * j + 2, v.z); sink(4 * j + 3, v.w);
+// Staging scheme of both kernels.  A tile slab is [E envs] x [C columns].  Each thread owns ONE
+// column and walks over envs with a fixed stride, so that
+//   * every address is base + compile-time offset: no per-element division or table lookup
+//     (the first version spent ~4400 instructions per warp, 3/4 of them index arithmetic, and was
+//     issue-bound at 20 us);
+//   * consecutive lanes touch consecutive floats of a row (coalesced 128-byte requests; for
+//     the contiguous buffers consecutive env groups are adjacent in memory as well);
+//   * all loads of a tile are issued into registers before the first one is consumed
+//     (memory-level parallelism is what bounds a one-wave, ~100-envs-per-SM kernel).
+template <int C, int E, int NT>
+struct ColSlab {
+  static constexpr int G = NT / C;                 // env groups that fit across the CTA
+  static constexpr int ACTIVE = G * C;             // threads that own a column
+  static constexpr int ITERS = (E + G - 1) / G;
+  static_assert(G >= 1, "tile narrower than a row");
+  float v[ITERS];
+  int col, grp;
+  bool on;
+  __device__ __forceinline__ ColSlab() : col(threadIdx.x % C), grp(threadIdx.x / C), on(threadIdx.x < ACTIVE) {}
+  // src_t: address of (env = grp, this thread's source column); row_stride in floats
+  __device__ __forceinline__ void load(const float* __restrict__ src_t, int row_stride, int nvalid) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+      if (on && grp + it * G < nvalid) v[it] = ld_stream1(src_t + (int64_t)(it * G) * row_stride);
   }
-  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += blockDim.x) sink(i, ld_stream1(src + i));
+  // dst_t: shared address of (env = grp, destination column)
+  __device__ __forceinline__ void drain(float* dst_t, int row_stride, int nvalid) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+      if (on && grp + it * G < nvalid) dst_t[it * G * row_stride] = v[it];
+  }
+};
+
+// contiguous [E, C] slab: shared tile -> global, thread-per-column
+template <int C, int E, int NT>
+__device__ __forceinline__ void col_store(float* __restrict__ dst_tile, const float* src_tile, int nvalid) {
+  ColSlab<C, E, NT> w;
+  float* dst = dst_tile + w.grp * C + w.col;
+  const float* src = src_tile + w.grp * C + w.col;
+#pragma unroll
+  for (int it = 0; it < w.ITERS; ++it)
+    if (w.on && w.grp + it * w.G < nvalid) dst[it * w.G * C] = src[it * w.G * C];
 }
 
-// cooperative tile store: Source(i) yields float i of the slab
-template <typename Source>
-__device__ __forceinline__ void slab_store(float* __restrict__ dst, int nfloats, Source&& src) {
-  const int n4 = nfloats >> 2;
-  float4* d4 = reinterpret_cast<float4*>(dst);
-  for (int j = threadIdx.x; j < n4; j += blockDim.x) {
-    float4 v;
-    v.x = src(4 * j); v.y = src(4 * j + 1); v.z = src(4 * j + 2); v.w = src(4 * j + 3);
-    st_stream4(d4 + j, v);
+// correctly rounded x / span from a correctly rounded reciprocal (Markstein): q = x*r,
+// q' = fma(fma(-q, span, x), r, q).  Three instructions instead of the ~12 of the IEEE division
+// sequence; outside a safe exponent window it falls back to __fdiv_rn.  Bit-equality with
+// __fdiv_rn is verified exhaustively over all 2^32 numerators for the shipped scale tables
+// (lg_selftest_division, tests/test_cuda_primitives.py).
+__device__ __forceinline__ float div_by_const(float num, float span, float rcp) {
+  const float a = fabsf(num);
+  if (a > 1e-30f && a < 1e30f) {
+    const float q = num * rcp;
+    const float r = __fmaf_rn(-q, span, num);
+    return __fmaf_rn(r, rcp, q);
   }
-  for (int i = (n4 << 2) + threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src(i);
+  return __fdiv_rn(num, span);
 }
 
 template <int A, bool ASYM, bool REWARD>
-__global__ void __launch_bounds__(kPostThreads)
+__global__ void __launch_bounds__(kPostThreads, 4)
 post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B, double sched_step_host) {
   using L = Layout<A, ASYM>;
-  constexpr int E = kTileEnvs;
-  __shared__ __align__(16) float s_raw[E * L::ROW];       // raw (unscaled) obs/state rows, state order
-  __shared__ __align__(16) float s_hist[E * LG_HISTORY_COLS];
+  constexpr int E = kTileEnvs;          // 32 envs per CTA
+  constexpr int NT = kPostThreads;      // 256 threads: warps 0-3 reward math (4 lanes per env),
+  constexpr int NR = E * kSubs;         //              warps 4-7 output columns (one thread per column)
+  static_assert(NT - NR >= L::ROW, "one output thread per state column");
+  __shared__ float s_raw[E * L::ROW];                      // raw (unscaled) obs/state rows, state order
+  __shared__ float s_hist[E * LG_HISTORY_COLS];
   __shared__ float s_tips[ASYM ? 1 : E * 9];               // symmetric mode: current fingertip positions
-  __shared__ float s_centre[L::ROW], s_span[L::ROW];
   __shared__ float s_coef[C_COUNT];
-  __shared__ double s_red[kPostThreads / 32][LG_NUM_STATS];
-  __shared__ int s_is_last;
+  __shared__ float s_stat[LG_NUM_STATS][E];
 
   const int tid = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * E;
   const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
 
-  // ---- per-CTA scalars -------------------------------------------------------------
-  for (int c = tid; c < L::ROW; c += kPostThreads) { s_centre[c] = P.scale_centre[c]; s_span[c] = P.scale_span[c]; }
-  if (REWARD && tid == 0) {
+  // ---- phase 1: issue every global load of the tile -----------------------------------------
+  constexpr int OBJ_COLS = ASYM ? 13 : 7;    // object root row (actor 4e+2)        trifinger_env.py:975, :1011, :1035
+  constexpr int TIP_COLS = ASYM ? 39 : 9;    // fingertip rows (bodies 6/11/16)     :974, :1040
+  ColSlab<TIP_COLS, E, NT> r_tip;
+  ColSlab<OBJ_COLS, E, NT> r_obj;
+  ColSlab<18, E, NT> r_dof;                  // dof_state [N,9,2]                   :1003-1007
+  ColSlab<LG_HISTORY_COLS, E, NT> r_hist;    // history entry 1 (previous step)
+  ColSlab<7, E, NT> r_goal;                  // goal pose buffer                    :1015
+  ColSlab<A, E, NT> r_act;                   // last action                         :1019
+  ColSlab<18, E, NT> r_ft;                   // fingertip wrenches                  :1051
+  ColSlab<9, E, NT> r_tq;                    // dof torque                          :1047
+  // gathers first: the scattered 52-byte rows have the longest queueing time
+  const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
+  {
+    constexpr int PER_TIP = ASYM ? 13 : 3;
+    const int tip = r_tip.col / PER_TIP, c = r_tip.col - tip * PER_TIP;
+    const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
+    r_tip.load(S.rigid_body + (e0 + r_tip.grp) * body_stride + body * 13 + c, body_stride, nvalid);
+  }
+  r_obj.load(S.root_state + (e0 + r_obj.grp) * actor_stride + P.object_slot * 13 + r_obj.col, actor_stride, nvalid);
+  r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
+  r_hist.load(B.history + (e0 + r_hist.grp) * LG_HISTORY_COLS + r_hist.col, LG_HISTORY_COLS, nvalid);
+  r_goal.load(B.goal_pose + (e0 + r_goal.grp) * 7 + r_goal.col, 7, nvalid);
+  r_act.load(B.action + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
+  if (ASYM) {
+    r_ft.load(S.ft_sensors + (e0 + r_ft.grp) * 18 + r_ft.col, 18, nvalid);
+    r_tq.load(S.dof_force + (e0 + r_tq.grp) * 9 + r_tq.col, 9, nvalid);
+  }
+  // per-env flags and counter of the reward leaders: in flight with everything else
+  const int env_r = tid >> 2, sub = tid & 3;
+  const bool leader = REWARD && tid < NR && sub == 0 && env_r < nvalid;
+  uint8_t in_goal_reset = 0, in_succ = 0, in_reset = 0;
+  int64_t in_steps = 0;
+  if (leader) {
+    const int64_t e = e0 + env_r;
+    in_goal_reset = B.goal_reset[e]; in_succ = B.successes[e]; in_reset = B.reset[e]; in_steps = B.steps_count[e];
+  }
+
+  // ---- per-CTA scalars (overlaps the loads) ---------------------------------------------------
+  if (REWARD && tid == NT - 1) {
     const double T = P.use_device_clock ? (double)(B.control->frame_count * P.global_num_envs) : sched_step_host;
     const LgRewardTerm* t = P.terms;
     s_coef[C_REACH] = (float)(t[0].weight * sched_gate(t[0], T));             // rewards.py:235
@@ -113,53 +186,26 @@ post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, cons
     s_coef[C_KP_SCALE] = (float)t[6].scale;
     s_coef[C_KP_EPS] = (float)t[6].eps;
   }
+  // the output threads' column and its scale_transform constants (torch_utils.py:33-36)
+  const int ocol = tid - NR;
+  const bool has_col = ocol >= 0 && ocol < L::ROW;
+  const float my_centre = has_col ? P.scale_centre[ocol] : 0.0f;
+  const float my_span = has_col ? P.scale_span[ocol] : 1.0f;
+  const float my_rcp = has_col ? P.scale_rcp[ocol] : 1.0f;
 
-  // ---- stage the tile: contiguous slabs with 128-bit loads -------------------------------
-  // dof_state [N,9,2] -> q (cols 0:9), qdot (cols 9:18)        trifinger_env.py:1003-1007
-  slab_load(S.dof_state + e0 * 18, nvalid * 18, [&](int i, float v) {
-    const int env = i / 18, r = i - env * 18;
-    s_raw[env * L::ROW + (r & 1) * 9 + (r >> 1)] = v;
-  });
-  // goal pose buffer -> cols 25:32                              trifinger_env.py:1015
-  slab_load(B.goal_pose + e0 * 7, nvalid * 7, [&](int i, float v) {
-    const int env = i / 7;
-    s_raw[env * L::ROW + L::OFF_GOAL + (i - env * 7)] = v;
-  });
-  // last action -> cols 32:32+A                                 trifinger_env.py:1019
-  slab_load(B.action + e0 * A, nvalid * A, [&](int i, float v) {
-    const int env = i / A;
-    s_raw[env * L::ROW + L::OFF_ACT + (i - env * A)] = v;
-  });
-  // previous fingertip positions + previous object pose (history entry 1)
-  slab_load(B.history + e0 * LG_HISTORY_COLS, nvalid * LG_HISTORY_COLS, [&](int i, float v) { s_hist[i] = v; });
+  // ---- phase 2: drain the registers into the state-ordered shared tile ------------------------
+  if (ASYM) r_tip.drain(s_raw + r_tip.grp * L::ROW + L::OFF_TIPS + r_tip.col, L::ROW, nvalid);
+  else r_tip.drain(s_tips + r_tip.grp * 9 + r_tip.col, 9, nvalid);
+  r_obj.drain(s_raw + r_obj.grp * L::ROW + (r_obj.col < 7 ? L::OFF_OBJ + r_obj.col : L::OFF_OBJVEL + (r_obj.col - 7)),
+              L::ROW, nvalid);
+  // (pos, vel) interleaved -> q cols 0:9, qdot cols 9:18
+  r_dof.drain(s_raw + r_dof.grp * L::ROW + (r_dof.col & 1) * 9 + (r_dof.col >> 1), L::ROW, nvalid);
+  r_hist.drain(s_hist + r_hist.grp * LG_HISTORY_COLS + r_hist.col, LG_HISTORY_COLS, nvalid);
+  r_goal.drain(s_raw + r_goal.grp * L::ROW + L::OFF_GOAL + r_goal.col, L::ROW, nvalid);
+  r_act.drain(s_raw + r_act.grp * L::ROW + L::OFF_ACT + r_act.col, L::ROW, nvalid);
   if (ASYM) {
-    slab_load(S.dof_force + e0 * 9, nvalid * 9, [&](int i, float v) {      // trifinger_env.py:1047
-      const int env = i / 9;
-      s_raw[env * L::ROW + L::OFF_TORQUE + (i - env * 9)] = v;
-    });
-    slab_load(S.ft_sensors + e0 * 18, nvalid * 18, [&](int i, float v) {   // trifinger_env.py:1051
-      const int env = i / 18;
-      s_raw[env * L::ROW + L::OFF_FT + (i - env * 18)] = v;
-    });
-  }
-  // ---- gathers: 52-byte rows out of the simulator tensors, consecutive lanes on consecutive floats
-  {
-    // object root row (actor 4e+2): pose -> cols 18:25, velocity -> state cols OBS:OBS+6   :975, :1011, :1035
-    constexpr int OBJ_COLS = ASYM ? 13 : 7;
-    for (int i = tid; i < nvalid * OBJ_COLS; i += kPostThreads) {
-      const int env = i / OBJ_COLS, c = i - env * OBJ_COLS;
-      const float v = ld_stream1(S.root_state + ((int64_t)P.actors_per_env * (e0 + env) + P.object_slot) * 13 + c);
-      s_raw[env * L::ROW + (c < 7 ? L::OFF_OBJ + c : L::OFF_OBJVEL + (c - 7))] = v;
-    }
-    // fingertip rows (bodies 6/11/16): full 13-float states when asymmetric, positions only otherwise  :974, :1040
-    constexpr int TIP_COLS = ASYM ? 13 : 3;
-    for (int i = tid; i < nvalid * 3 * TIP_COLS; i += kPostThreads) {
-      const int env = i / (3 * TIP_COLS), r = i - env * (3 * TIP_COLS);
-      const int tip = r / TIP_COLS, c = r - tip * TIP_COLS;
-      const float v = ld_stream1(S.rigid_body + ((e0 + env) * P.bodies_per_env + P.fingertip_body[tip]) * 13 + c);
-      if (ASYM) s_raw[env * L::ROW + L::OFF_TIPS + r] = v;
-      else s_tips[env * 9 + r] = v;
-    }
+    r_ft.drain(s_raw + r_ft.grp * L::ROW + L::OFF_FT + r_ft.col, L::ROW, nvalid);
+    r_tq.drain(s_raw + r_tq.grp * L::ROW + L::OFF_TORQUE + r_tq.col, L::ROW, nvalid);
   }
   __syncthreads();
 
@@ -167,12 +213,66 @@ post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, cons
     return ASYM ? s_raw[env * L::ROW + L::OFF_TIPS + tip * 13 + c] : s_tips[env * 9 + tip * 3 + c];
   };
 
-  // ---- rewards / termination: 4 lanes per env, each one sub-task, combined by shuffles ---------
-  if (REWARD) {
-    const int env = tid >> 2, sub = tid & 3;
+  if (tid >= NR) {
+    // ======== output warps: thread c owns column c of every env: states[:, c], obs[:, c] for c < OBS =====
+    if (has_col) {
+      const bool norm = P.normalize_obs != 0;
+      const float clip = P.clip_obs;
+      float* st_out = ASYM ? B.states + e0 * L::STATE + ocol : nullptr;                     // trifinger_env.py:990-994
+      float* ob_out = ocol < L::OBS ? B.obs + e0 * L::OBS + ocol : nullptr;                 // trifinger_env.py:983-987
+      float* stc_out = (ASYM && B.states_clipped) ? B.states_clipped + e0 * L::STATE + ocol : nullptr;  // vec_task.py:147
+      float* obc_out = (ocol < L::OBS && B.obs_clipped) ? B.obs_clipped + e0 * L::OBS + ocol : nullptr; // vec_task.py:167
+      const float* src = s_raw + ocol;
+      auto value = [&](int env) -> float {
+        const float v = src[env * L::ROW];
+        return norm ? div_by_const(2.0f * (v - my_centre), my_span, my_rcp) : v;
+      };
+      if (stc_out == nullptr && obc_out == nullptr) {
+#pragma unroll 8
+        for (int env = 0; env < E; ++env) {
+          if (env < nvalid) {
+            const float v = value(env);
+            if (ASYM) st_out[env * L::STATE] = v;
+            if (ob_out) ob_out[env * L::OBS] = v;
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int env = 0; env < E; ++env) {
+          if (env < nvalid) {
+            const float v = value(env);
+            const float vc = fminf(fmaxf(v, -clip), clip);
+            if (ASYM) st_out[env * L::STATE] = v;
+            if (ob_out) ob_out[env * L::OBS] = v;
+            if (stc_out) stc_out[env * L::STATE] = vc;
+            if (obc_out) obc_out[env * L::OBS] = vc;
+          }
+        }
+      }
+    }
+    // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step
+    {
+      constexpr int NO = NT - NR, G = NO / LG_HISTORY_COLS, ITERS = (E + G - 1) / G;
+      const int ot = tid - NR, c = ot & 15, grp = ot >> 4;
+      float* dst = B.history + (e0 + grp) * LG_HISTORY_COLS + c;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int env = grp + it * G;
+        if (env < nvalid)
+          dst[it * G * LG_HISTORY_COLS] = c < 9 ? tip_pos(env, c / 3, c % 3) : s_raw[env * L::ROW + L::OFF_OBJ + (c - 9)];
+      }
+    }
+    return;
+  }
+  if (!REWARD) return;
+
+  // ======== reward warps: 4 lanes per env, each one sub-task, combined by shuffles =======================
+  {
+    const int env = env_r;
     const bool live = env < nvalid;
     const float* row = s_raw + env * L::ROW;
     const float* hist = s_hist + env * LG_HISTORY_COLS;
+    const int64_t e = e0 + env;
     float va = 0.0f, vb = 0.0f, vc = 0.0f, vd = 0.0f;  // sub-task results
     if (live) {
       const float ox = row[L::OFF_OBJ], oy = row[L::OFF_OBJ + 1], oz = row[L::OFF_OBJ + 2];
@@ -231,129 +331,71 @@ post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, cons
     const float theta = __shfl_sync(full, vb, base + 2);
     const float theta_prev_abs = __shfl_sync(full, vb, base + 3);
 
-    double st[LG_NUM_STATS];
+    if (sub == 0) {
+      float st[LG_NUM_STATS];
 #pragma unroll
-    for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0;
-    if (live && sub == 0) {
-      const int64_t e = e0 + env;
-      const float t_reach = va;
-      // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
-      const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - theta_prev_abs));
-      const float terms[6] = {t_reach, t_move, t_dist, t_rot, t_delta, t_objmove};
-      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
+      for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0f;
+      if (live) {
+        const float t_reach = va;
+        // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
+        const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - theta_prev_abs));
+        const float terms[6] = {t_reach, t_move, t_dist, t_rot, t_delta, t_objmove};
+        float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        if (P.terms[k].activate) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = (double)terms[k]; }
-        if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
+        for (int k = 0; k < 6; ++k) {
+          if (P.terms[k].activate) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = terms[k]; }
+          if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
+        }
+        // __check_termination (trifinger_env.py:1053-1099)
+        const bool pos_ok = dist <= s_coef[C_POS_TOL];
+        const bool rot_ok = theta <= s_coef[C_ROT_TOL];
+        bool done;
+        if (P.task_difficulty < 4) done = pos_ok;
+        else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
+        else done = rot_ok;
+        bool goal_reset = in_goal_reset != 0;
+        bool succ = in_succ != 0;
+        if (P.success_activate) {
+          if (done) reward = reward + s_coef[C_BONUS];
+          goal_reset = done;
+          succ = succ || goal_reset;
+          B.goal_reset[e] = goal_reset;
+        } else {
+          succ = goal_reset && succ;
+        }
+        B.successes[e] = succ;
+        B.reward[e] = reward;
+        // step counter, timeout, dones (envs/env_base.py:391-399)
+        bool reset = in_reset != 0;
+        if (P.fuse_bookkeeping) {
+          const int64_t steps = in_steps + 1;
+          B.steps_count[e] = steps;
+          if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
+          B.reset[e] = reset;
+        }
+        const bool dn = reset && goal_reset;
+        if (B.dones) B.dones[e] = dn;
+        st[LG_STAT_POSITION_GOAL] = pos_ok;
+        st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
+        st[LG_STAT_SUCCESSES] = succ;
+        st[LG_STAT_REWARD] = reward;
+        st[LG_STAT_RESETS] = reset;
+        st[LG_STAT_DONES] = dn;
       }
-      // __check_termination (trifinger_env.py:1053-1099)
-      const bool pos_ok = dist <= s_coef[C_POS_TOL];
-      const bool rot_ok = theta <= s_coef[C_ROT_TOL];
-      bool done;
-      if (P.task_difficulty < 4) done = pos_ok;
-      else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
-      else done = rot_ok;
-      bool goal_reset = B.goal_reset[e] != 0;
-      bool succ = B.successes[e] != 0;
-      if (P.success_activate) {
-        if (done) reward = reward + s_coef[C_BONUS];
-        goal_reset = done;
-        succ = succ || goal_reset;
-        B.goal_reset[e] = goal_reset;
-      } else {
-        succ = goal_reset && succ;
-      }
-      B.successes[e] = succ;
-      B.reward[e] = reward;
-      // step counter, timeout, dones (envs/env_base.py:391-399)
-      bool reset = B.reset[e] != 0;
-      if (P.fuse_bookkeeping) {
-        const int64_t steps = B.steps_count[e] + 1;
-        B.steps_count[e] = steps;
-        if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
-        B.reset[e] = reset;
-      }
-      const bool dn = reset && goal_reset;
-      if (B.dones) B.dones[e] = dn;
-      st[LG_STAT_POSITION_GOAL] = pos_ok;
-      st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
-      st[LG_STAT_SUCCESSES] = succ;
-      st[LG_STAT_REWARD] = (double)reward;
-      st[LG_STAT_RESETS] = reset;
-      st[LG_STAT_DONES] = dn;
+#pragma unroll
+      for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
     }
-    // episode statistics: fp64 warp tree over the 8 env-leader lanes, then one RED per slot per CTA
-#pragma unroll
-    for (int i = 0; i < LG_NUM_STATS; ++i) {
-      if (i == 6 || i > LG_STAT_DONES) continue;  // keypoint slot / unused
-      double v = st[i];
-      v += __shfl_xor_sync(full, v, 4);
-      v += __shfl_xor_sync(full, v, 8);
-      v += __shfl_xor_sync(full, v, 16);
-      if ((tid & 31) == 0) s_red[tid >> 5][i] = v;
-    }
-  }
-
-  // ---- outputs: scale_transform (torch_utils.py:33-36) fused into 128-bit slab stores -----------
-  const bool norm = P.normalize_obs != 0;
-  auto scaled = [&](int env, int c) -> float {
-    const float v = s_raw[env * L::ROW + c];
-    return norm ? scale_transform(v, s_centre[c], s_span[c]) : v;
-  };
-  const float clip = P.clip_obs;
-  slab_store(B.obs + e0 * L::OBS, nvalid * L::OBS, [&](int i) {          // trifinger_env.py:983-987
-    const int env = i / L::OBS;
-    return scaled(env, i - env * L::OBS);
-  });
-  if (B.obs_clipped)
-    slab_store(B.obs_clipped + e0 * L::OBS, nvalid * L::OBS, [&](int i) {  // wrappers/vec_task.py:167
-      const int env = i / L::OBS;
-      return fminf(fmaxf(scaled(env, i - env * L::OBS), -clip), clip);
-    });
-  if (ASYM) {
-    slab_store(B.states + e0 * L::STATE, nvalid * L::STATE, [&](int i) {  // trifinger_env.py:990-994
-      const int env = i / L::STATE;
-      return scaled(env, i - env * L::STATE);
-    });
-    if (B.states_clipped)
-      slab_store(B.states_clipped + e0 * L::STATE, nvalid * L::STATE, [&](int i) {  // vec_task.py:147
-        const int env = i / L::STATE;
-        return fminf(fmaxf(scaled(env, i - env * L::STATE), -clip), clip);
-      });
-  }
-  // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step
-  slab_store(B.history + e0 * LG_HISTORY_COLS, nvalid * LG_HISTORY_COLS, [&](int i) {
-    const int env = i >> 4, c = i & 15;
-    return c < 9 ? tip_pos(env, c / 3, c % 3) : s_raw[env * L::ROW + L::OFF_OBJ + (c - 9)];
-  });
-
-  // ---- statistics epilogue: the last CTA to finish publishes sums and `_step_info` --------------
-  if (REWARD) {
-    __syncthreads();
-    if (tid < LG_NUM_STATS) {
-      double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < kPostThreads / 32; ++w) v += s_red[w][tid];
-      if (!(tid == 6 || tid > LG_STAT_DONES)) atomicAdd(B.stats_accum + tid, v);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_is_last = (atomicAdd(&B.control->post_done, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_is_last) {
-      __threadfence();
-      if (tid < LG_NUM_STATS) {
-        const unsigned long long bits = atomicExch(reinterpret_cast<unsigned long long*>(B.stats_accum + tid), 0ull);
-        const double v = __longlong_as_double((long long)bits);
-        B.stats[tid] = v;
-        // reward-term and success entries are means (trifinger_env.py:554, :1098), the rest counts (:1067, :1076)
-        const bool is_mean = tid < LG_STAT_POSITION_GOAL || tid == LG_STAT_SUCCESSES || tid == LG_STAT_REWARD;
-        B.step_info[tid] = is_mean ? (float)(v / (double)P.num_envs) : (float)v;
-      }
-      if (tid == 0) {
-        B.control->post_done = 0;
-        B.control->rng_epoch += 1;  // fresh random numbers for the next step's resets
-      }
+    // ---- episode statistics: per-CTA fp64 sums in a fixed order, one RED per slot, no fence ----------
+    asm volatile("bar.sync 1, %0;" :: "n"(NR) : "memory");  // the four reward warps only
+    if (tid <= LG_STAT_DONES) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < E; ++k) acc += (double)s_stat[tid][k];
+      // reward-term, reward and success entries are means over this shard (trifinger_env.py:554, :1098),
+      // the rest are counts (:1067, :1076)
+      const bool is_mean = tid < LG_STAT_POSITION_GOAL || tid == LG_STAT_SUCCESSES || tid == LG_STAT_REWARD;
+      if (is_mean) acc = acc / (double)P.num_envs;
+      atomicAdd(B.step_stats + tid, acc);
     }
   }
 }
@@ -425,6 +467,7 @@ struct TileScan {
 };
 
 // Resolves the global exclusive prefix; the last tile re-arms ticket and epoch for the next launch.
+template <bool TICKET>
 __device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* status, const TileScan& t, int num_tiles,
                                                  uint32_t& ex_a, uint32_t& ex_b, int32_t* counts_out) {
   __shared__ uint32_t s_ex[2];
@@ -436,8 +479,7 @@ __device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* statu
       if (t.tile == num_tiles - 1) {
         // every tile has read the epoch and taken its ticket by now (their aggregates are visible)
         if (counts_out) { counts_out[0] = (int32_t)(a + t.total_a); counts_out[1] = (int32_t)(b + t.total_b); }
-        ctl->scan_ticket = 0;
-        __threadfence();
+        if (TICKET) { ctl->scan_ticket = 0; __threadfence(); }
         ctl->scan_epoch = t.epoch + 1;
       }
     }
@@ -446,37 +488,77 @@ __device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* statu
   ex_a = s_ex[0]; ex_b = s_ex[1];
 }
 
-__global__ void __launch_bounds__(kPreThreads)
-pre_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B,
-                   const float* __restrict__ action_in, int num_tiles) {
-  const int tid = threadIdx.x;
-  // tiles are handed out by ticket so that every predecessor of a tile is already running
-  __shared__ int s_tile;
-  __shared__ uint32_t s_epoch;
-  if (tid == 0) {
-    s_epoch = ld_volatile_u32(&B.control->scan_epoch);
-    s_tile = (int)atomicAdd(&B.control->scan_ticket, 1u);
+// Cold path of the pre-physics kernel, kept out of line so that the no-reset step fetches and
+// executes none of the sampler / Philox code (trifinger_env.py:373-440).
+__device__ __noinline__ void reset_cold(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
+                                        bool f_reset, bool f_goal, int64_t rank_reset, int64_t rank_goal,
+                                        uint64_t epoch) {
+  if (f_reset) {
+    const DrawSource dr = make_draws(P, epoch, e, kPurposeReset, B.inject_reset_u, B.inject_reset_n, rank_reset);
+    reset_one_env(P, S, B, e, dr);
   }
-  __syncthreads();
-  const int tile = s_tile;
-  const uint32_t epoch = s_epoch;
-  const int64_t e = (int64_t)tile * kPreThreads + tid;
-  const bool live = e < P.num_envs;
-  const bool f_reset = live && B.reset[e] != 0;
-  const bool f_goal = live && B.goal_reset[e] != 0;
+  if (f_goal) {  // goal reset second, as in env_base.py:374-379
+    const DrawSource dr = make_draws(P, epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n, rank_goal);
+    B.goal_reset[e] = 0;  // trifinger_env.py:427
+    apply_goal_sample(P, S, B, e, dr);
+  }
+}
 
-  // ---- block scan + aggregate publication ---------------------------------------------------
-  __shared__ uint32_t s_wa[kPreThreads / 32], s_wb[kPreThreads / 32];
+template <int A, bool TICKET>
+__global__ void __launch_bounds__(kPreThreads)
+pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
+                   const __grid_constant__ LgBuffers B,
+                   const float* __restrict__ action_in, int num_tiles) {
+  constexpr int E = kPreThreads, NT = kPreThreads;
+  __shared__ float s_act[E * A];
+  __shared__ float s_dof[E * 18];
+  __shared__ float s_tq[E * 9];
+  __shared__ int s_tile;
+  __shared__ uint32_t s_wa[NT / 32], s_wb[NT / 32];
+  const int tid = threadIdx.x;
+  // every thread reads the epoch before the tile publishes anything, so the last tile may advance it
+  const uint32_t epoch = ld_volatile_u32(&B.control->scan_epoch);
+  int tile = blockIdx.x;
+  if (TICKET) {  // grids larger than what is co-resident: tiles by ticket, so predecessors always run
+    if (tid == 0) s_tile = (int)atomicAdd(&B.control->scan_ticket, 1u);
+    __syncthreads();
+    tile = s_tile;
+  }
+  const int64_t e0 = (int64_t)tile * E;
+  const int64_t e = e0 + tid;
+  const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
+  const bool live = tid < nvalid;
+  const bool want_torque = B.applied_torque != nullptr;
+
+  // ---- every global load of the tile up front ---------------------------------------------------
+  uint8_t flag_r = 0, flag_g = 0;
+  if (live) { flag_r = B.reset[e]; flag_g = B.goal_reset[e]; }
+  ColSlab<A, E, NT> r_act;
+  ColSlab<18, E, NT> r_dof;
+  r_act.load(action_in + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
+  if (want_torque) r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
+  if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
+
+  // ---- block scan of both masks + aggregate publication (env_base.py:374-379) -------------------
+  const bool f_reset = flag_r != 0, f_goal = flag_g != 0;
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned ba = __ballot_sync(0xffffffffu, f_reset), bb = __ballot_sync(0xffffffffu, f_goal);
   if (lane == 0) { s_wa[warp] = __popc(ba); s_wb[warp] = __popc(bb); }
+  // action store (envs/env_base.py:369) with the wrapper's clamp (wrappers/vec_task.py:162)
+  if (P.clip_input_actions) {
+    const float clip = P.clip_actions;
+#pragma unroll
+    for (int it = 0; it < r_act.ITERS; ++it) r_act.v[it] = fminf(fmaxf(r_act.v[it], -clip), clip);
+  }
+  r_act.drain(s_act + r_act.grp * A + r_act.col, A, nvalid);
+  if (want_torque) r_dof.drain(s_dof + r_dof.grp * 18 + r_dof.col, 18, nvalid);
   __syncthreads();
   TileScan t;
   t.tile = tile; t.epoch = epoch;
   {
     uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
 #pragma unroll
-    for (int w = 0; w < kPreThreads / 32; ++w) {
+    for (int w = 0; w < NT / 32; ++w) {
       if (w < warp) { pa += s_wa[w]; pb += s_wb[w]; }
       ta += s_wa[w]; tb += s_wb[w];
     }
@@ -490,40 +572,32 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const
     atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
                (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
   }
-
-  const uint64_t rng_epoch = B.control->rng_epoch;
   uint32_t ex_a = 0, ex_b = 0;
   const bool need_rank_first = P.inject_draws != 0;  // injected draws are indexed by compaction rank
-  if (need_rank_first) tile_scan_finish(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
+  if (need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
 
-  // ---- action store (envs/env_base.py:369; clamp of wrappers/vec_task.py:162) -------------------
-  float act[LG_MAX_ACTION_DIM];
-  if (live) {
-    const int A = P.action_dim;
-    for (int c = 0; c < A; ++c) {
-      float a = action_in[e * A + c];
-      if (P.clip_input_actions) a = fminf(fmaxf(a, -P.clip_actions), P.clip_actions);
-      act[c] = f_reset ? 0.0f : a;  // reset zeroes the row after the store (trifinger_env.py:387)
-      B.action[e * A + c] = act[c];
+  // ---- resets (cold) -------------------------------------------------------------------------------
+  if (f_reset || f_goal) {
+    if (f_reset) {
+#pragma unroll
+      for (int c = 0; c < A; ++c) s_act[tid * A + c] = 0.0f;  // the row is zeroed after the store (:387)
     }
-  }
-  // ---- resets (trifinger_env.py:373-440); goal reset second, as in env_base.py:374-379 ----------
-  if (f_reset) {
-    const DrawSource dr = make_draws(P, rng_epoch, e, kPurposeReset, B.inject_reset_u, B.inject_reset_n,
-                                     (int64_t)ex_a + t.rank_a);
-    reset_one_env(P, S, B, e, dr);
-  }
-  if (f_goal) {
-    const DrawSource dr = make_draws(P, rng_epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
-                                     (int64_t)ex_b + t.rank_b);
-    B.goal_reset[e] = 0;  // trifinger_env.py:427
-    apply_goal_sample(P, S, B, e, dr);
+    reset_cold(P, S, B, e, f_reset, f_goal, (int64_t)ex_a + t.rank_a, (int64_t)ex_b + t.rank_b, (uint64_t)epoch);
   }
   // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
-  if (live && B.applied_torque) torque_one_env(P, act, S.dof_state + e * 18, B.applied_torque + e * 9);
+  if (want_torque && live) {
+    float act[A];
+#pragma unroll
+    for (int c = 0; c < A; ++c) act[c] = s_act[tid * A + c];
+    const bool dof_rewritten = f_reset && P.robot_reset != LG_RESET_NONE;
+    torque_one_env(P, act, dof_rewritten ? S.dof_state + e * 18 : s_dof + tid * 18, s_tq + tid * 9);
+  }
+  __syncthreads();
+  col_store<A, E, NT>(B.action + e0 * A, s_act, nvalid);
+  if (want_torque) col_store<9, E, NT>(B.applied_torque + e0 * 9, s_tq, nvalid);
 
   // ---- ordered id lists (env_base.py:374-379; trifinger_env.py:413-416, :435-436) ---------------
-  if (!need_rank_first) tile_scan_finish(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
+  if (!need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
   if (f_reset) {
     const int64_t j = (int64_t)ex_a + t.rank_a;
     const int32_t base = (int32_t)(P.actors_per_env * e);
@@ -572,7 +646,7 @@ compact_kernel(const uint8_t* __restrict__ mask, int64_t n, int64_t* __restrict_
     atomicExch(reinterpret_cast<unsigned long long*>(status + t.tile),
                (unsigned long long)pack_status(t.epoch, t.tile == 0 ? kStateInclusive : kStateAggregate, tot, 0));
   uint32_t ex_a, ex_b;
-  tile_scan_finish(ctl, status, t, num_tiles, ex_a, ex_b, counts2);
+  tile_scan_finish<true>(ctl, status, t, num_tiles, ex_a, ex_b, counts2);
   if (f) ids[(int64_t)ex_a + t.rank_a] = e;
 }
 
@@ -582,7 +656,7 @@ __global__ void reset_ids_kernel(const __grid_constant__ LgParams P, const LgSim
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < k) {
     const int64_t e = ids[j];
-    const uint64_t epoch = B.control->rng_epoch;
+    const uint64_t epoch = B.control->rng_epoch | (1ull << 63);  // never collides with the fused path's epochs
     if (goal_only) {
       const DrawSource dr = make_draws(P, epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n, j);
       B.goal_reset[e] = 0;
@@ -660,6 +734,18 @@ __global__ void keypoints_kernel(const float* pose, float size, float* out, int6
   out[i * 3] = p[0] + rx; out[i * 3 + 1] = p[1] + ry; out[i * 3 + 2] = p[2] + rz;
 }
 
+// exhaustive check of div_by_const against IEEE division for one (span, rcp): all 2^32 numerators
+__global__ void selftest_division_kernel(float span, float rcp, unsigned long long* mismatches) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (uint64_t bits = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bits < (1ull << 32); bits += stride) {
+    const float x = __uint_as_float((uint32_t)bits);
+    const float a = div_by_const(x, span, rcp), b = __fdiv_rn(x, span);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace lg
 
 // =========================================================================================
@@ -696,8 +782,11 @@ int validate(const LgParams* P, const LgSimState* S, const LgBuffers* B, bool ne
 template <bool REWARD>
 int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, double sched, cudaStream_t st) {
   if (int rc = validate(P, S, B, true)) return rc;
-  if (REWARD && (!B->stats_accum || !B->stats || !B->step_info))
-    return fail(LG_ERR_BAD_ARG, "null statistics buffer");
+  if (REWARD && !B->step_stats) return fail(LG_ERR_BAD_ARG, "null statistics buffer");
+  if (REWARD && !P->fuse_bookkeeping) {
+    // stand-alone _post_step: nobody zeroed the accumulators (lg_pre_physics does in the fused sequence)
+    if (cudaMemsetAsync(B->step_stats, 0, LG_NUM_STATS * sizeof(double), st) != cudaSuccess) return check_launch("memset");
+  }
   const int grid = (int)((P->num_envs + lg::kTileEnvs - 1) / lg::kTileEnvs);
   const bool asym = P->asymmetric_obs != 0;
 #define LG_LAUNCH(AD, AS) lg::post_physics_kernel<AD, AS, REWARD><<<grid, lg::kPostThreads, 0, st>>>(*P, *S, *B, sched)
@@ -746,7 +835,14 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
   if (P->inject_draws && !(B->inject_reset_u || B->inject_goal_u || B->inject_reset_n || B->inject_goal_n))
     return fail(LG_ERR_BAD_ARG, "inject_draws set without injected arrays");
   const int tiles = (int)lg_scan_tiles(P->num_envs);
-  lg::pre_physics_kernel<<<tiles, lg::kPreThreads, 0, (cudaStream_t)stream>>>(*P, *S, *B, action_in, tiles);
+  if (!aligned16(action_in)) return fail(LG_ERR_BAD_ARG, "action_in must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  // all tiles co-resident (<= 8 CTAs on each of 148 SMs): tiles are block indices; beyond that, tickets
+  const bool ticket = tiles > 148 * 8;
+#define LG_PRE(AD, TK) lg::pre_physics_kernel<AD, TK><<<tiles, lg::kPreThreads, 0, st>>>(*P, *S, *B, action_in, tiles)
+  if (P->action_dim == 9) { if (ticket) LG_PRE(9, true); else LG_PRE(9, false); }
+  else { if (ticket) LG_PRE(18, true); else LG_PRE(18, false); }
+#undef LG_PRE
   return check_launch("pre_physics_kernel");
 }
 
@@ -818,6 +914,12 @@ int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n,
   if (!pose || !out || n < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
   if (n) lg::keypoints_kernel<<<LG_GRID(n * 8)>>>(pose, cube_size, out, n);
   return check_launch("keypoints_kernel");
+}
+
+int lg_selftest_division(float span, float rcp, unsigned long long* mismatches_dev, void* stream) {
+  if (!mismatches_dev) return fail(LG_ERR_BAD_ARG, "null argument");
+  lg::selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(span, rcp, mismatches_dev);
+  return check_launch("selftest_division_kernel");
 }
 
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {

@@ -287,9 +287,7 @@ class TrifingerEnv(IsaacEnvBase):
         self._applied_torque = torch.zeros((N, 9), device=dev, dtype=torch.float)
         self._term_rewards = None
         self._obs_clipped = self._states_clipped = None
-        self._stats_accum = torch.zeros(nat.LG_NUM_STATS, device=dev, dtype=torch.float64)
-        self._stats = torch.zeros(nat.LG_NUM_STATS, device=dev, dtype=torch.float64)
-        self._step_info_buf = torch.zeros(nat.LG_NUM_STATS, device=dev, dtype=torch.float)
+        self._step_stats = torch.zeros(nat.LG_NUM_STATS, device=dev, dtype=torch.float64)
         self._reset_ids = torch.zeros(N, device=dev, dtype=torch.long)
         self._goal_reset_ids = torch.zeros(N, device=dev, dtype=torch.long)
         self._counts = torch.zeros(2, **i32)
@@ -335,7 +333,7 @@ class TrifingerEnv(IsaacEnvBase):
         b.steps_count = p(self._steps_count_buf)
         b.goal_pose, b.goal_movement, b.history = p(self._object_goal_poses_buf), p(self._object_goal_movement_buf), p(self._history)
         b.applied_torque, b.term_rewards = p(self._applied_torque), p(self._term_rewards)
-        b.stats_accum, b.stats, b.step_info = p(self._stats_accum), p(self._stats), p(self._step_info_buf)
+        b.step_stats = p(self._step_stats)
         b.reset_ids, b.goal_reset_ids, b.counts = p(self._reset_ids), p(self._goal_reset_ids), p(self._counts)
         b.robot_indices, b.reset_root_indices, b.goal_root_indices = p(self._robot_indices), p(self._reset_root_indices), p(self._goal_root_indices)
         b.scan_status, b.control = p(self._scan_status), p(self._control)
@@ -377,9 +375,12 @@ class TrifingerEnv(IsaacEnvBase):
         self._inject = {}
         for kind, pair in (("reset", reset), ("goal", goal)):
             if pair is not None:
-                u = torch.as_tensor(np.nan_to_num(np.asarray(pair[0], dtype=np.float32)), device=dev).contiguous()
-                n = torch.as_tensor(np.nan_to_num(np.asarray(pair[1], dtype=np.float32)), device=dev).contiguous()
-                self._inject[kind] = (u, n)
+                def up(a, cols):
+                    a = np.nan_to_num(np.asarray(a, dtype=np.float32)).reshape(-1, cols)
+                    if a.shape[0] == 0:  # an empty list still needs a valid device pointer
+                        a = np.zeros((1, cols), np.float32)
+                    return torch.as_tensor(a, device=dev).contiguous()
+                self._inject[kind] = (up(pair[0], nat.LG_INJECT_U_COLS), up(pair[1], nat.LG_INJECT_N_COLS))
         self._apply_injection()
 
     def _apply_injection(self):
@@ -432,9 +433,10 @@ class TrifingerEnv(IsaacEnvBase):
         return self._obs_buf, self._reward_buf, self._dones, self._step_info
 
     def _make_info(self) -> Dict[str, torch.Tensor]:
-        """`_step_info` of the reference (trifinger_env.py:554, :1068, :1076, :1099) as 0-d views
-        of the per-step statistics buffer (values are this shard's; see global_step_info)."""
-        buf, info = self._step_info_buf, {}
+        """`_step_info` of the reference (trifinger_env.py:554, :1068, :1076, :1099) as 0-d fp64 views
+        of the per-step statistics buffer: valid until the next step overwrites them; values are
+        this shard's (see global_step_info)."""
+        buf, info = self._step_stats, {}
         for i, name in enumerate(nat.TERM_NAMES[:6]):
             if self.config["reward_terms"][name]["activate"]:
                 info[f"env/rewards/{name}"] = buf[i]
@@ -446,7 +448,11 @@ class TrifingerEnv(IsaacEnvBase):
     def global_step_info(self) -> Dict[str, float]:
         """Whole-job statistics: all-reduces the 16 shard sums (the only cross-GPU traffic of the
         path) and divides by the global env count.  Synchronises the host."""
-        sums = self._stats.clone()
+        local_n = float(self.num_instances)
+        is_mean = torch.zeros(nat.LG_NUM_STATS, device=self._torch_device, dtype=torch.float64)
+        is_mean[:7] = 1.0
+        is_mean[nat.STAT_SUCCESSES] = is_mean[nat.STAT_REWARD] = 1.0
+        sums = self._step_stats * (is_mean * local_n + (1.0 - is_mean))  # means -> sums; counts stay
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)

@@ -166,8 +166,9 @@ def build_params(cfg: dict, num_local_envs: int, env_offset: int = 0, global_num
     lo, hi = state_scale(cfg) if cfg["asymmetric_obs"] else observation_scale(cfg)
     centre = ((lo + hi) * F(0.5)).astype(F)   # torch: (lower + upper) * 0.5 in fp32
     span = (hi - lo).astype(F)                # torch: upper - lower in fp32
+    rcp = (F(1.0) / span).astype(F)           # IEEE fp32 division: the correctly rounded reciprocal
     for i in range(len(lo)):
-        p.scale_centre[i], p.scale_span[i] = centre[i], span[i]
+        p.scale_centre[i], p.scale_span[i], p.scale_rcp[i] = centre[i], span[i], rcp[i]
     a_lo, a_hi = action_scale(mode)
     for i in range(A):
         p.action_low[i], p.action_high[i] = a_lo[i], a_hi[i]
