@@ -82,6 +82,8 @@ typedef struct LgRewardTerm {
 
 /* Everything the kernels need from the env config. Plain data, passed by value. */
 typedef struct LgParams {
+  /* ---- hot block: everything the per-step kernels read on their critical path sits in the first
+   * 160 bytes (two constant-cache lines), ahead of the cold tables ---- */
   int64_t num_envs;         /* envs held by this process (the shard)                            */
   int64_t env_offset;       /* global index of local env 0 (sharding; keys the RNG)             */
   int64_t global_num_envs;  /* env count of the whole job: env_steps_count = frames x this
@@ -99,6 +101,23 @@ typedef struct LgParams {
   int32_t goal_rotation;    /* goal_movement.rotation.activate (trifinger_env.py:1248-1253)      */
   int32_t success_activate; /* termination_conditions.success.activate (trifinger_env.py:1088)   */
   int32_t control_decimation;
+  /* simulator layout (trifinger_env.py:811-825, :881-883; SURVEY.md §A.1) */
+  int32_t bodies_per_env;   /* 20 */
+  int32_t actors_per_env;   /* 4  */
+  int32_t fingertip_body[3];/* 6, 11, 16 */
+  int32_t robot_slot, object_slot, goal_slot; /* 0, 2, 3 */
+  /* wrapper clipping (wrappers/vec_task.py:146-170); used only for the *_clipped outputs */
+  float clip_obs, clip_actions;
+  int32_t clip_input_actions; /* clamp the incoming action to +-clip_actions (vec_task.py:162) */
+  int32_t dr_activate;      /* extension: domain-randomisation noise (all sigmas zero = off)    */
+  int32_t inject_draws;     /* test hook: read uniforms/normals from LgBuffers.inject_* */
+  int32_t use_device_clock; /* frame count and reward coefficients come from device memory
+                               (LgControl / LgBuffers.reward_coef): CUDA-graph replay           */
+  int32_t fuse_bookkeeping; /* lg_post_physics also does steps += 1, timeout and dones
+                               (env_base.py:391-399); 0 = _post_step semantics only              */
+  int32_t term_active_mask; /* bit k = terms[k].activate                                        */
+  uint64_t seed;
+  /* ---- cold block ---- */
   double dt;                /* config["sim"]["dt"]                                               */
   double success_bonus, position_tolerance, orientation_tolerance;
   double dof_pos_stddev, dof_vel_stddev, goal_rate_magnitude;
@@ -116,26 +135,17 @@ typedef struct LgParams {
   float dof_default_pos[9], dof_default_vel[9];
   /* cube geometry (envs/trifinger/utils.py:54-131), python doubles as the reference holds them */
   double cube_half_size, cube_radius_3d, cube_max_height, max_com_distance;
-  /* simulator layout (trifinger_env.py:811-825, :881-883; SURVEY.md §A.1) */
-  int32_t bodies_per_env;   /* 20 */
-  int32_t actors_per_env;   /* 4  */
-  int32_t fingertip_body[3];/* 6, 11, 16 */
-  int32_t robot_slot, object_slot, goal_slot; /* 0, 2, 3 */
-  /* wrapper clipping (wrappers/vec_task.py:146-170); used only for the *_clipped outputs */
-  float clip_obs, clip_actions;
-  int32_t clip_input_actions; /* clamp the incoming action to +-clip_actions (vec_task.py:162) */
-  /* extension: domain-randomisation noise, raw channels, sigma per column; all-zero = off */
-  int32_t dr_activate;
   float dr_action_sigma;
   float dr_sigma[LG_MAX_STATE_DIM];
-  /* RNG */
-  uint64_t seed;
-  int32_t inject_draws;     /* test hook: read uniforms/normals from LgBuffers.inject_* */
-  int32_t use_device_clock; /* take the frame count from LgControl (CUDA-graph replay)              */
-  int32_t fuse_bookkeeping; /* lg_post_physics also does steps += 1, timeout and dones
-                               (env_base.py:391-399); 0 = _post_step semantics only              */
   int32_t _pad_tail;
 } LgParams;
+
+/* Scalar coefficients of the reward terms for ONE value of env_steps_count: the Python-float
+ * arithmetic of the reward modules (weights x schedule gates x dt, rewards.py:56-63, :123-139, :169-184),
+ * rounded to fp32 where the reference hands the scalar to an fp32 tensor op.  Computed on the host by
+ * lg_post_physics, or on the device by lg_pre_physics when P.use_device_clock is set. */
+#define LG_NUM_COEF 20
+typedef struct LgCoef { float v[LG_NUM_COEF]; } LgCoef;
 
 /* Device-resident control block (one per env shard; zero-initialised by the caller). */
 typedef struct LgControl {
@@ -187,6 +197,10 @@ typedef struct LgBuffers {
   int32_t* goal_root_indices;  /* [N]  goal actor indices for the goal-reset envs               */
   uint64_t* scan_status;    /* [lg_scan_tiles(N)] look-back status words (workspace)            */
   LgControl* control;
+  float* reward_coef;       /* [LG_NUM_COEF] device copy of LgCoef, written by lg_pre_physics when
+                               P.use_device_clock (optional otherwise)                              */
+  const float* scale_table; /* [3, LG_MAX_STATE_DIM] device copy of P.scale_centre | scale_span | scale_rcp
+                               (coalesced reads; the parameter block is a constant bank)             */
   /* test hook (P.inject_draws): canonical draw arrays indexed by compaction rank */
   const float* inject_reset_u;  /* [k, 24] robot noise 0:18 | object r,theta,yaw | goal u0,u1,u2 */
   const float* inject_reset_n;  /* [k, 8]  goal quaternion 0:4 | ang-vel axis 4:7 | magnitude 7  */
@@ -258,9 +272,11 @@ int lg_saturate(const float* x, const float* lower, const float* upper, float* o
                 int64_t n, int32_t dims, void* stream);                                     /* :60-75   */
 int lg_lgsk_kernel(const float* x, float scale, float* out, int64_t n, void* stream);       /* rewards.py:20-34 */
 
-/* Self-test: counts numerators x (all 2^32 bit patterns) for which the kernels' fast division by
- * `span` (using `rcp` = fp32(1/span)) differs from IEEE x / span.  Expected result: 0. */
-int lg_selftest_division(float span, float rcp, unsigned long long* mismatches_dev, void* stream);
+/* Self-test of the kernels' fast division by `span` (with `rcp` = fp32(1/span)) over all 2^32 numerators.
+ * out_dev[0] = numerators with 2^-100 <= |x| < 2^100 or x = 0 whose quotient is not bit-identical to IEEE
+ * x / span (expected 0); out_dev[1] = worst ulp distance for 0 < |x| < 2^-100 (expected <= 1);
+ * out_dev[2] = numerators >= 2^100 / inf the range guard failed to flag (expected 0).  out_dev: 3 x uint64. */
+int lg_selftest_division(float span, float rcp, unsigned long long* out_dev, void* stream);
 
 /* Extension (no reference code): world-frame cube corners, [n,7] poses -> [n,8,3] keypoints. */
 int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n, void* stream);

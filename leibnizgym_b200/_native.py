@@ -20,6 +20,7 @@ LG_NUM_STATS = 16
 LG_INJECT_U_COLS = 24
 LG_INJECT_N_COLS = 8
 LG_HISTORY_COLS = 16
+LG_NUM_COEF = 20
 
 TERM_NAMES = ("finger_reach_object_rate", "finger_move_penalty", "object_dist", "object_rot",
               "object_rot_delta", "object_move", "keypoint")
@@ -44,6 +45,11 @@ class LgParams(C.Structure):
         ("normalize_action", C.c_int32), ("command_mode", C.c_int32), ("apply_safety_damping", C.c_int32),
         ("task_difficulty", C.c_int32), ("robot_reset", C.c_int32), ("object_reset", C.c_int32),
         ("goal_rotation", C.c_int32), ("success_activate", C.c_int32), ("control_decimation", C.c_int32),
+        ("bodies_per_env", C.c_int32), ("actors_per_env", C.c_int32), ("fingertip_body", C.c_int32 * 3),
+        ("robot_slot", C.c_int32), ("object_slot", C.c_int32), ("goal_slot", C.c_int32),
+        ("clip_obs", C.c_float), ("clip_actions", C.c_float), ("clip_input_actions", C.c_int32),
+        ("dr_activate", C.c_int32), ("inject_draws", C.c_int32), ("use_device_clock", C.c_int32),
+        ("fuse_bookkeeping", C.c_int32), ("term_active_mask", C.c_int32), ("seed", C.c_uint64),
         ("dt", C.c_double), ("success_bonus", C.c_double), ("position_tolerance", C.c_double),
         ("orientation_tolerance", C.c_double), ("dof_pos_stddev", C.c_double), ("dof_vel_stddev", C.c_double),
         ("goal_rate_magnitude", C.c_double),
@@ -56,12 +62,7 @@ class LgParams(C.Structure):
         ("dof_default_pos", C.c_float * 9), ("dof_default_vel", C.c_float * 9),
         ("cube_half_size", C.c_double), ("cube_radius_3d", C.c_double), ("cube_max_height", C.c_double),
         ("max_com_distance", C.c_double),
-        ("bodies_per_env", C.c_int32), ("actors_per_env", C.c_int32), ("fingertip_body", C.c_int32 * 3),
-        ("robot_slot", C.c_int32), ("object_slot", C.c_int32), ("goal_slot", C.c_int32),
-        ("clip_obs", C.c_float), ("clip_actions", C.c_float), ("clip_input_actions", C.c_int32),
-        ("dr_activate", C.c_int32), ("dr_action_sigma", C.c_float), ("dr_sigma", C.c_float * LG_MAX_STATE_DIM),
-        ("seed", C.c_uint64), ("inject_draws", C.c_int32), ("use_device_clock", C.c_int32),
-        ("fuse_bookkeeping", C.c_int32), ("_pad_tail", C.c_int32),
+        ("dr_action_sigma", C.c_float), ("dr_sigma", C.c_float * LG_MAX_STATE_DIM), ("_pad_tail", C.c_int32),
     ]
 
 
@@ -80,7 +81,7 @@ class LgBuffers(C.Structure):
         "obs", "states", "obs_clipped", "states_clipped", "action", "reward", "reset", "goal_reset",
         "successes", "dones", "steps_count", "goal_pose", "goal_movement", "history", "applied_torque",
         "term_rewards", "step_stats", "reset_ids", "goal_reset_ids", "counts",
-        "robot_indices", "reset_root_indices", "goal_root_indices", "scan_status", "control",
+        "robot_indices", "reset_root_indices", "goal_root_indices", "scan_status", "control", "reward_coef", "scale_table",
         "inject_reset_u", "inject_reset_n", "inject_goal_u", "inject_goal_n")]
 
 

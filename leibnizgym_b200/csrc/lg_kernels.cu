@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "lg_device.cuh"
 
@@ -21,7 +22,6 @@ namespace lg {
 // =========================================================================================
 // post-physics: one CTA = one tile of E envs, 4 threads per env
 // =========================================================================================
-constexpr int kSubs = 4;
 constexpr int kTileEnvs = 32;
 constexpr int kPostThreads = 256;
 
@@ -36,19 +36,42 @@ struct Layout {
 
 // coefficient slots computed once per CTA (python-float arithmetic of the reward modules)
 enum Coef { C_REACH = 0, C_MOVE, C_DIST, C_ROT_SCALE, C_ROT_SCHED, C_ROT_W, C_DELTA_RAMP, C_DELTA_W,
-            C_OBJMOVE, C_DT, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_COUNT };
+            C_OBJMOVE, C_DT, C_DT_RCP, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_COUNT };
 
-__device__ __forceinline__ double sched_gate(const LgRewardTerm& t, double T) {  // rewards.py:56-60
+__host__ __device__ inline double sched_gate(const LgRewardTerm& t, double T) {  // rewards.py:56-60
   if (t.sched_start != t.sched_end) return (t.sched_start <= T && T <= t.sched_end) ? 1.0 : 0.0;
   return 1.0;
 }
-__device__ __forceinline__ double sched_ramp(const LgRewardTerm& t, double T) {  // rewards.py:14-17, :169-172
+__host__ __device__ inline double sched_ramp(const LgRewardTerm& t, double T) {  // rewards.py:14-17, :169-172
   if (t.sched_start != t.sched_end) {
     const double v = (T - t.sched_start) / (t.sched_end - t.sched_start);
-    return fmax(0.0, fmin(1.0, v));
+    return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
   }
   return 1.0;
 }
+// The reward modules' Python-float arithmetic for env_steps_count = T.  Same code on host and device
+// (IEEE double in both places), so the two clock modes produce identical coefficients.
+__host__ __device__ inline void compute_coefs(const LgParams& P, double T, float* c) {
+  const LgRewardTerm* t = P.terms;
+  c[C_REACH] = (float)(t[0].weight * sched_gate(t[0], T));             // rewards.py:235
+  c[C_MOVE] = (float)t[1].weight;                                       // rewards.py:263
+  c[C_DIST] = (float)((t[2].weight * P.dt) * sched_gate(t[2], T));     // rewards.py:63
+  c[C_ROT_SCALE] = (float)t[3].scale;                                   // rewards.py:137
+  c[C_ROT_SCHED] = (float)(sched_gate(t[3], T) * P.dt);
+  c[C_ROT_W] = (float)t[3].weight;                                      // rewards.py:139
+  c[C_DELTA_RAMP] = (float)sched_ramp(t[4], T);                         // rewards.py:182
+  c[C_DELTA_W] = (float)t[4].weight;                                    // rewards.py:184
+  c[C_OBJMOVE] = (float)t[5].weight;                                    // rewards.py:91
+  c[C_DT] = (float)P.dt;
+  c[C_DT_RCP] = 1.0f / (float)P.dt;                                     // IEEE division: correctly rounded
+  c[C_POS_TOL] = (float)P.position_tolerance;
+  c[C_ROT_TOL] = (float)P.orientation_tolerance;
+  c[C_BONUS] = (float)P.success_bonus;
+  c[C_KP_W] = (float)(t[6].weight * P.dt);
+  c[C_KP_SCALE] = (float)t[6].scale;
+  c[C_KP_EPS] = (float)t[6].eps;
+}
+static_assert(C_COUNT <= LG_NUM_COEF, "LgCoef too small");
 
 // Staging scheme of both kernels.  A tile slab is [E envs] x [C columns].  Each thread owns ONE
 // column and walks over envs with a fixed stride, so that
@@ -69,17 +92,21 @@ struct ColSlab {
   int col, grp;
   bool on;
   __device__ __forceinline__ ColSlab() : col(threadIdx.x % C), grp(threadIdx.x / C), on(threadIdx.x < ACTIVE) {}
+  // number of envs this thread visits: grp, grp+G, ... < nvalid
+  __device__ __forceinline__ int trips(int nvalid) const { return on ? (nvalid - grp + G - 1) / G : 0; }
   // src_t: address of (env = grp, this thread's source column); row_stride in floats
   __device__ __forceinline__ void load(const float* __restrict__ src_t, int row_stride, int nvalid) {
+    const int n = trips(nvalid);
 #pragma unroll
     for (int it = 0; it < ITERS; ++it)
-      if (on && grp + it * G < nvalid) v[it] = ld_stream1(src_t + (int64_t)(it * G) * row_stride);
+      if (it < n) v[it] = ld_stream1(src_t + (int64_t)(it * G) * row_stride);
   }
   // dst_t: shared address of (env = grp, destination column)
   __device__ __forceinline__ void drain(float* dst_t, int row_stride, int nvalid) {
+    const int n = trips(nvalid);
 #pragma unroll
     for (int it = 0; it < ITERS; ++it)
-      if (on && grp + it * G < nvalid) dst_t[it * G * row_stride] = v[it];
+      if (it < n) dst_t[it * G * row_stride] = v[it];
   }
 };
 
@@ -94,310 +121,372 @@ __device__ __forceinline__ void col_store(float* __restrict__ dst_tile, const fl
     if (w.on && w.grp + it * w.G < nvalid) dst[it * w.G * C] = src[it * w.G * C];
 }
 
-// correctly rounded x / span from a correctly rounded reciprocal (Markstein): q = x*r,
-// q' = fma(fma(-q, span, x), r, q).  Three instructions instead of the ~12 of the IEEE division
-// sequence; outside a safe exponent window it falls back to __fdiv_rn.  Bit-equality with
-// __fdiv_rn is verified exhaustively over all 2^32 numerators for the shipped scale tables
-// (lg_selftest_division, tests/test_cuda_primitives.py).
-__device__ __forceinline__ float div_by_const(float num, float span, float rcp) {
-  const float a = fabsf(num);
-  if (a > 1e-30f && a < 1e30f) {
-    const float q = num * rcp;
-    const float r = __fmaf_rn(-q, span, num);
-    return __fmaf_rn(r, rcp, q);
+// Fast division by a per-column constant: q = x*r, q' = fma(fma(-q, span, x), r, q) with r = fp32(1/span)
+// correctly rounded (Markstein).  Contract, verified exhaustively by lg_selftest_division over all 2^32
+// numerators for every span the env uses:
+//   * 2^-100 <= |x| < 2^100 : bit-identical to IEEE x / span;
+//   * x = +-0                : 0 (a negative zero comes out as +0);
+//   * 0 < |x| < 2^-100       : within 1 ulp (the residual may be subnormal);
+//   * |x| >= 2^100, inf      : flagged through `amax`; the caller redoes the column with __fdiv_rn.
+__device__ __forceinline__ float div_by_const(float num, float span, float rcp, float& amax) {
+  const float q = num * rcp;
+  const float r = __fmaf_rn(-q, span, num);
+  amax = fmaxf(amax, fabsf(num));
+  return __fmaf_rn(r, rcp, q);
+}
+constexpr float kDivSafeMax = 1.2676506e30f;  // 2^100
+
+// Cold path: re-emit one lane's output column with IEEE division (only when a numerator left the fast
+// division's window).  Re-reads the source so the hot path keeps its registers.
+template <int STATE, int OBS, bool ASYM>
+__device__ __noinline__ void output_exact(const LgParams& P, const LgBuffers& B, const float* src, int stride, int cnt,
+                                          int64_t env0, int dcol) {
+  const float centre = P.scale_centre[dcol], span = P.scale_span[dcol], clip = P.clip_obs;
+  for (int k = 0; k < cnt; ++k) {
+    const int64_t e = env0 + k;
+    const float raw = src[(int64_t)k * stride];
+    const float v = P.normalize_obs ? __fdiv_rn(2.0f * (raw - centre), span) : raw;
+    const float vc = fminf(fmaxf(v, -clip), clip);
+    if (ASYM) B.states[e * STATE + dcol] = v;
+    if (dcol < OBS) B.obs[e * OBS + dcol] = v;
+    if (ASYM && B.states_clipped) B.states_clipped[e * STATE + dcol] = vc;
+    if (dcol < OBS && B.obs_clipped) B.obs_clipped[e * OBS + dcol] = vc;
   }
-  return __fdiv_rn(num, span);
 }
 
-template <int A, bool ASYM, bool REWARD>
+// One lane = one OUTPUT column of the tile ("role"), walking over the envs of its part of the tile.
+// The role fixes, per lane and once per launch: the source pointer and row stride, the output column
+// with its scale constants, and where (if anywhere) the raw value is staged for the reward math.
+// The per-element code is then identical for every lane — no divergence although the lanes of a warp
+// read from seven different tensors — and free of index arithmetic:
+//     load   v[k] = src[k * stride]                       (all loads of the tile in flight at once)
+//     emit   states[k][dcol] = obs[k][dcol] = scale(v[k])  (compile-time row offsets)
+// Role order = output column order of the states row, except that the nine fingertip POSITION columns
+// come right after the observation columns: the lanes that feed obs, the reward staging and the next
+// history entry are then all in the first two warps of a part, and the other warps skip that code.
+template <int A, bool ASYM>
+struct Roles {
+  static constexpr int OBS = 32 + A;
+  static constexpr int R_TIPPOS = OBS;                  // 9 roles
+  static constexpr int R_TIPREST = R_TIPPOS + 9;        // 30 roles (asymmetric only)
+  static constexpr int R_OBJVEL = R_TIPREST + 30;       // 6
+  static constexpr int R_FT = R_OBJVEL + 6;             // 18
+  static constexpr int R_TQ = R_FT + 18;                // 9
+  static constexpr int R_END = ASYM ? R_TQ + 9 : R_TIPREST;
+  static constexpr int LANES = R_END <= 64 ? 64 : 128;  // role lanes per tile part
+  static constexpr int PARTS = kPostThreads / LANES;    // the tile's envs are split over the parts
+  static constexpr int EP = kTileEnvs / PARTS;          // envs per lane
+  static constexpr int FRONT = R_TIPREST;               // roles < FRONT may feed obs / staging / history
+  static_assert(R_END <= LANES, "more output columns than role lanes");
+};
+
+template <int A, bool ASYM, bool REWARD, bool CLIP>
 __global__ void __launch_bounds__(kPostThreads, 4)
-post_physics_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B, double sched_step_host) {
+post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
+                    const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
   using L = Layout<A, ASYM>;
+  using R = Roles<A, ASYM>;
   constexpr int E = kTileEnvs;          // 32 envs per CTA
-  constexpr int NT = kPostThreads;      // 256 threads: warps 0-3 reward math (4 lanes per env),
-  constexpr int NR = E * kSubs;         //              warps 4-7 output columns (one thread per column)
-  static_assert(NT - NR >= L::ROW, "one output thread per state column");
-  __shared__ float s_raw[E * L::ROW];                      // raw (unscaled) obs/state rows, state order
-  __shared__ float s_hist[E * LG_HISTORY_COLS];
-  __shared__ float s_tips[ASYM ? 1 : E * 9];               // symmetric mode: current fingertip positions
+  constexpr int NT = kPostThreads;      // 256 threads; after the barrier warps 0-3 do the reward math
+  constexpr int EP = R::EP;
+  constexpr int HS = LG_HISTORY_COLS + 1;  // padded row: lane-per-env reads stay conflict free
+  // only what the reward terms read is staged in shared memory (raw, unscaled)
+  __shared__ float s_obj[E * 7];        // object pose
+  __shared__ float s_goal[E * 7];       // goal pose
+  __shared__ float s_tips[E * 9];       // fingertip positions
+  __shared__ float s_hist[E * HS];      // previous fingertip positions (9) + previous object pose (7)
   __shared__ float s_coef[C_COUNT];
-  __shared__ float s_stat[LG_NUM_STATS][E];
+  __shared__ float s_part[8][E];        // sub-task results of the reward warps
+  __shared__ float s_stat[LG_NUM_STATS][E + 1];
 
   const int tid = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * E;
   const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
 
-  // ---- phase 1: issue every global load of the tile -----------------------------------------
-  constexpr int OBJ_COLS = ASYM ? 13 : 7;    // object root row (actor 4e+2)        trifinger_env.py:975, :1011, :1035
-  constexpr int TIP_COLS = ASYM ? 39 : 9;    // fingertip rows (bodies 6/11/16)     :974, :1040
-  ColSlab<TIP_COLS, E, NT> r_tip;
-  ColSlab<OBJ_COLS, E, NT> r_obj;
-  ColSlab<18, E, NT> r_dof;                  // dof_state [N,9,2]                   :1003-1007
-  ColSlab<LG_HISTORY_COLS, E, NT> r_hist;    // history entry 1 (previous step)
-  ColSlab<7, E, NT> r_goal;                  // goal pose buffer                    :1015
-  ColSlab<A, E, NT> r_act;                   // last action                         :1019
-  ColSlab<18, E, NT> r_ft;                   // fingertip wrenches                  :1051
-  ColSlab<9, E, NT> r_tq;                    // dof torque                          :1047
-  // gathers first: the scattered 52-byte rows have the longest queueing time
-  const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
+  // ---- role of this lane ---------------------------------------------------------------------------
+  int role = tid % R::LANES;
+  if (role >= R::R_END) role -= (R::LANES - R::R_END);  // spare lanes duplicate a column (same value, same address)
+  const bool front = (tid % R::LANES) / 32 * 32 < R::FRONT;  // warp-uniform: this warp holds obs/stage/history roles
+  const int env_first = (tid / R::LANES) * EP;     // first env (within the tile) of this lane's part
+  const float* src;             // source of (env_first, column)
+  int stride;                   // source row stride in floats
+  int dcol;                     // output column (scaled): states[:, dcol], obs[:, dcol] if dcol < OBS; -1: none
+  float* stage = nullptr;       // shared destination of env_first's raw value, or null
+  int stage_stride = 0;
+  int hist_col = -1;            // column of the NEXT history entry this lane provides, or -1
   {
-    constexpr int PER_TIP = ASYM ? 13 : 3;
-    const int tip = r_tip.col / PER_TIP, c = r_tip.col - tip * PER_TIP;
-    const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
-    r_tip.load(S.rigid_body + (e0 + r_tip.grp) * body_stride + body * 13 + c, body_stride, nvalid);
+    const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
+    auto tip_src = [&](int tip, int c) {
+      const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
+      return S.rigid_body + body * 13 + c;
+    };
+    if (role < 18) {                                         // dof_state (pos, vel) interleaved  trifinger_env.py:1003-1007
+      src = S.dof_state + role; stride = 18;
+      dcol = (role & 1) * 9 + (role >> 1);
+    } else if (role < 25) {                                  // object pose (root row of actor 4e+2)  :975, :1011
+      const int c = role - 18;
+      src = S.root_state + P.object_slot * 13 + c; stride = actor_stride;
+      dcol = L::OFF_OBJ + c;
+      stage = s_obj + c; stage_stride = 7; hist_col = 9 + c;
+    } else if (role < 32) {                                  // goal pose buffer                  :1015
+      const int c = role - 25;
+      src = B.goal_pose + c; stride = 7;
+      dcol = L::OFF_GOAL + c;
+      stage = s_goal + c; stage_stride = 7;
+    } else if (role < R::OBS) {                              // last action                       :1019
+      const int c = role - 32;
+      src = B.action + c; stride = A;
+      dcol = L::OFF_ACT + c;
+    } else if (role < R::R_TIPREST) {                        // fingertip positions (bodies 6/11/16)  :974, :1040
+      const int j = role - R::R_TIPPOS, tip = j / 3, c = j - tip * 3;
+      src = tip_src(tip, c); stride = body_stride;
+      dcol = ASYM ? L::OFF_TIPS + tip * 13 + c : -1;
+      stage = s_tips + j; stage_stride = 9; hist_col = j;
+    } else if (role < R::R_OBJVEL) {                         // fingertip orientation + velocity
+      const int j = role - R::R_TIPREST, tip = j / 10, c = 3 + (j - tip * 10);
+      src = tip_src(tip, c); stride = body_stride;
+      dcol = L::OFF_TIPS + tip * 13 + c;
+    } else if (role < R::R_FT) {                             // object velocity                   :1035
+      const int c = role - R::R_OBJVEL;
+      src = S.root_state + P.object_slot * 13 + 7 + c; stride = actor_stride;
+      dcol = L::OFF_OBJVEL + c;
+    } else if (role < R::R_TQ) {                             // fingertip wrenches                :1051
+      const int c = role - R::R_FT;
+      src = S.ft_sensors + c; stride = 18;
+      dcol = L::OFF_FT + c;
+    } else {                                                 // dof torque                        :1047
+      const int c = role - R::R_TQ;
+      src = S.dof_force + c; stride = 9;
+      dcol = L::OFF_TORQUE + c;
+    }
   }
-  r_obj.load(S.root_state + (e0 + r_obj.grp) * actor_stride + P.object_slot * 13 + r_obj.col, actor_stride, nvalid);
-  r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
-  r_hist.load(B.history + (e0 + r_hist.grp) * LG_HISTORY_COLS + r_hist.col, LG_HISTORY_COLS, nvalid);
-  r_goal.load(B.goal_pose + (e0 + r_goal.grp) * 7 + r_goal.col, 7, nvalid);
-  r_act.load(B.action + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
-  if (ASYM) {
-    r_ft.load(S.ft_sensors + (e0 + r_ft.grp) * 18 + r_ft.col, 18, nvalid);
-    r_tq.load(S.dof_force + (e0 + r_tq.grp) * 9 + r_tq.col, 9, nvalid);
+  src += (e0 + env_first) * stride;
+  const int cnt = max(0, min(EP, nvalid - env_first));   // envs of this lane: env_first .. env_first + cnt - 1
+  const bool full = nvalid == E;                           // every CTA but possibly the last
+
+  // ---- phase 1: every global load of the tile in flight -----------------------------------------
+  float v[EP];
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < EP; ++k) v[k] = ld_stream1(src + (int64_t)k * stride);
+  } else {
+#pragma unroll
+    for (int k = 0; k < EP; ++k) v[k] = k < cnt ? ld_stream1(src + (int64_t)k * stride) : 0.0f;
   }
-  // per-env flags and counter of the reward leaders: in flight with everything else
-  const int env_r = tid >> 2, sub = tid & 3;
-  const bool leader = REWARD && tid < NR && sub == 0 && env_r < nvalid;
+  // reward warps: thread (w, env) = (tid / 32, tid % 32), w < 4.  Each fetches one 16-byte piece of the
+  // env's previous history entry (64-byte rows), warp 0 also the env's flags and step counter.
+  const int rw = tid >> 5, renv = tid & 31;
+  const bool rlive = REWARD && rw < 4 && renv < nvalid;
+  float4 hprev = make_float4(0.f, 0.f, 0.f, 0.f);
   uint8_t in_goal_reset = 0, in_succ = 0, in_reset = 0;
   int64_t in_steps = 0;
-  if (leader) {
-    const int64_t e = e0 + env_r;
-    in_goal_reset = B.goal_reset[e]; in_succ = B.successes[e]; in_reset = B.reset[e]; in_steps = B.steps_count[e];
+  if (rlive) {
+    hprev = ld_stream4(reinterpret_cast<const float4*>(B.history + (e0 + renv) * LG_HISTORY_COLS) + rw);
+    if (rw == 0) {
+      const int64_t e = e0 + renv;
+      in_goal_reset = B.goal_reset[e]; in_succ = B.successes[e]; in_reset = B.reset[e]; in_steps = B.steps_count[e];
+    }
+  }
+  // this lane's scale_transform constants (torch_utils.py:33-36) in half-span form:
+  // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
+  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
+  if (P.normalize_obs && dcol >= 0) {
+    centre = __ldg(B.scale_table + dcol);
+    half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
+    rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
   }
 
-  // ---- per-CTA scalars (overlaps the loads) ---------------------------------------------------
-  if (REWARD && tid == NT - 1) {
-    const double T = P.use_device_clock ? (double)(B.control->frame_count * P.global_num_envs) : sched_step_host;
-    const LgRewardTerm* t = P.terms;
-    s_coef[C_REACH] = (float)(t[0].weight * sched_gate(t[0], T));             // rewards.py:235
-    s_coef[C_MOVE] = (float)t[1].weight;                                       // rewards.py:263
-    s_coef[C_DIST] = (float)((t[2].weight * P.dt) * sched_gate(t[2], T));     // rewards.py:63
-    s_coef[C_ROT_SCALE] = (float)t[3].scale;                                   // rewards.py:137
-    s_coef[C_ROT_SCHED] = (float)(sched_gate(t[3], T) * P.dt);
-    s_coef[C_ROT_W] = (float)t[3].weight;                                      // rewards.py:139
-    s_coef[C_DELTA_RAMP] = (float)sched_ramp(t[4], T);                         // rewards.py:182
-    s_coef[C_DELTA_W] = (float)t[4].weight;                                    // rewards.py:184
-    s_coef[C_OBJMOVE] = (float)t[5].weight;                                    // rewards.py:91
-    s_coef[C_DT] = (float)P.dt;
-    s_coef[C_POS_TOL] = (float)P.position_tolerance;
-    s_coef[C_ROT_TOL] = (float)P.orientation_tolerance;
-    s_coef[C_BONUS] = (float)P.success_bonus;
-    s_coef[C_KP_W] = (float)(t[6].weight * P.dt);
-    s_coef[C_KP_SCALE] = (float)t[6].scale;
-    s_coef[C_KP_EPS] = (float)t[6].eps;
-  }
-  // the output threads' column and its scale_transform constants (torch_utils.py:33-36)
-  const int ocol = tid - NR;
-  const bool has_col = ocol >= 0 && ocol < L::ROW;
-  const float my_centre = has_col ? P.scale_centre[ocol] : 0.0f;
-  const float my_span = has_col ? P.scale_span[ocol] : 1.0f;
-  const float my_rcp = has_col ? P.scale_rcp[ocol] : 1.0f;
+  // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----
+  if (REWARD && tid < C_COUNT) s_coef[tid] = P.use_device_clock ? __ldg(B.reward_coef + tid) : CF.v[tid];
 
-  // ---- phase 2: drain the registers into the state-ordered shared tile ------------------------
-  if (ASYM) r_tip.drain(s_raw + r_tip.grp * L::ROW + L::OFF_TIPS + r_tip.col, L::ROW, nvalid);
-  else r_tip.drain(s_tips + r_tip.grp * 9 + r_tip.col, 9, nvalid);
-  r_obj.drain(s_raw + r_obj.grp * L::ROW + (r_obj.col < 7 ? L::OFF_OBJ + r_obj.col : L::OFF_OBJVEL + (r_obj.col - 7)),
-              L::ROW, nvalid);
-  // (pos, vel) interleaved -> q cols 0:9, qdot cols 9:18
-  r_dof.drain(s_raw + r_dof.grp * L::ROW + (r_dof.col & 1) * 9 + (r_dof.col >> 1), L::ROW, nvalid);
-  r_hist.drain(s_hist + r_hist.grp * LG_HISTORY_COLS + r_hist.col, LG_HISTORY_COLS, nvalid);
-  r_goal.drain(s_raw + r_goal.grp * L::ROW + L::OFF_GOAL + r_goal.col, L::ROW, nvalid);
-  r_act.drain(s_raw + r_act.grp * L::ROW + L::OFF_ACT + r_act.col, L::ROW, nvalid);
-  if (ASYM) {
-    r_ft.drain(s_raw + r_ft.grp * L::ROW + L::OFF_FT + r_ft.col, L::ROW, nvalid);
-    r_tq.drain(s_raw + r_tq.grp * L::ROW + L::OFF_TORQUE + r_tq.col, L::ROW, nvalid);
+  // ---- phase 2: stage what the reward terms read, then ONE barrier -------------------------------
+  // Only the warps that hold staged columns wait for (a small part of) their data here; the others
+  // reach the barrier right after issuing their loads.  The reward math then runs on warps 0-3 while
+  // the bulk of the tile is still arriving and being scaled and stored by warps 4-7.
+  if (rlive) {
+    float* h = s_hist + renv * HS + rw * 4;
+    h[0] = hprev.x; h[1] = hprev.y; h[2] = hprev.z; h[3] = hprev.w;
+  }
+  if (front && stage) {
+    float* dst = stage + env_first * stage_stride;
+#pragma unroll
+    for (int k = 0; k < EP; ++k)
+      if (full || k < cnt) dst[k * stage_stride] = v[k];
   }
   __syncthreads();
 
-  auto tip_pos = [&](int env, int tip, int c) -> float {
-    return ASYM ? s_raw[env * L::ROW + L::OFF_TIPS + tip * 13 + c] : s_tips[env * 9 + tip * 3 + c];
-  };
-
-  if (tid >= NR) {
-    // ======== output warps: thread c owns column c of every env: states[:, c], obs[:, c] for c < OBS =====
-    if (has_col) {
-      const bool norm = P.normalize_obs != 0;
-      const float clip = P.clip_obs;
-      float* st_out = ASYM ? B.states + e0 * L::STATE + ocol : nullptr;                     // trifinger_env.py:990-994
-      float* ob_out = ocol < L::OBS ? B.obs + e0 * L::OBS + ocol : nullptr;                 // trifinger_env.py:983-987
-      float* stc_out = (ASYM && B.states_clipped) ? B.states_clipped + e0 * L::STATE + ocol : nullptr;  // vec_task.py:147
-      float* obc_out = (ocol < L::OBS && B.obs_clipped) ? B.obs_clipped + e0 * L::OBS + ocol : nullptr; // vec_task.py:167
-      const float* src = s_raw + ocol;
-      auto value = [&](int env) -> float {
-        const float v = src[env * L::ROW];
-        return norm ? div_by_const(2.0f * (v - my_centre), my_span, my_rcp) : v;
-      };
-      if (stc_out == nullptr && obc_out == nullptr) {
-#pragma unroll 8
-        for (int env = 0; env < E; ++env) {
-          if (env < nvalid) {
-            const float v = value(env);
-            if (ASYM) st_out[env * L::STATE] = v;
-            if (ob_out) ob_out[env * L::OBS] = v;
-          }
-        }
-      } else {
-#pragma unroll 4
-        for (int env = 0; env < E; ++env) {
-          if (env < nvalid) {
-            const float v = value(env);
-            const float vc = fminf(fmaxf(v, -clip), clip);
-            if (ASYM) st_out[env * L::STATE] = v;
-            if (ob_out) ob_out[env * L::OBS] = v;
-            if (stc_out) stc_out[env * L::STATE] = vc;
-            if (obc_out) obc_out[env * L::OBS] = vc;
-          }
-        }
-      }
-    }
-    // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step
-    {
-      constexpr int NO = NT - NR, G = NO / LG_HISTORY_COLS, ITERS = (E + G - 1) / G;
-      const int ot = tid - NR, c = ot & 15, grp = ot >> 4;
-      float* dst = B.history + (e0 + grp) * LG_HISTORY_COLS + c;
+  // ---- phase 3 (all warps; the reward warps come back to it after their math) -------------------------
+  auto emit_outputs = [&]() {
+    // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step.
+    // After the barrier: every read of the previous entry has completed.
+    if (front && hist_col >= 0) {
+      float* dst = B.history + (e0 + env_first) * LG_HISTORY_COLS + hist_col;
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int env = grp + it * G;
-        if (env < nvalid)
-          dst[it * G * LG_HISTORY_COLS] = c < 9 ? tip_pos(env, c / 3, c % 3) : s_raw[env * L::ROW + L::OFF_OBJ + (c - 9)];
-      }
+      for (int k = 0; k < EP; ++k)
+        if (full || k < cnt) dst[k * LG_HISTORY_COLS] = v[k];
     }
-    return;
-  }
-  if (!REWARD) return;
-
-  // ======== reward warps: 4 lanes per env, each one sub-task, combined by shuffles =======================
-  {
-    const int env = env_r;
-    const bool live = env < nvalid;
-    const float* row = s_raw + env * L::ROW;
-    const float* hist = s_hist + env * LG_HISTORY_COLS;
-    const int64_t e = e0 + env;
-    float va = 0.0f, vb = 0.0f, vc = 0.0f, vd = 0.0f;  // sub-task results
+    float amax = 0.0f;  // largest numerator seen: beyond 2^100 (never, for physical data) the column is redone exactly
+    const float clip = P.clip_obs;
+    const int st_off = env_first * L::STATE + dcol, ob_off = env_first * L::OBS + dcol;
+    float* st = ASYM ? B.states + e0 * L::STATE + st_off : nullptr;                          // trifinger_env.py:990-994
+    float* stc = (CLIP && ASYM) ? B.states_clipped + e0 * L::STATE + st_off : nullptr;       // vec_task.py:147
+#pragma unroll
+    for (int k = 0; k < EP; ++k) v[k] = div_by_const(v[k] - centre, half_span, rcp_half, amax);
+    if (ASYM) {
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (full || k < cnt) {
+          st[k * L::STATE] = v[k];
+          if (CLIP) stc[k * L::STATE] = fminf(fmaxf(v[k], -clip), clip);
+        }
+    }
+    if (front && dcol >= 0 && dcol < L::OBS) {
+      float* ob = B.obs + e0 * L::OBS + ob_off;                                              // trifinger_env.py:983-987
+      float* obc = CLIP ? B.obs_clipped + e0 * L::OBS + ob_off : nullptr;                    // vec_task.py:167
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (full || k < cnt) {
+          ob[k * L::OBS] = v[k];
+          if (CLIP) obc[k * L::OBS] = fminf(fmaxf(v[k], -clip), clip);
+        }
+    }
+    if (dcol >= 0 && !(amax < kDivSafeMax))  // cold: same addresses, same thread: plain overwrite
+      output_exact<L::STATE, L::OBS, ASYM>(P, B, src, stride, cnt, e0 + env_first, dcol);
+  };
+  // ======== reward warps: lane = env, warp = sub-task (uniform control flow inside a warp) ================
+  if (REWARD && rw < 4) {
+    const int env = renv;
+    const bool live = renv < nvalid;
+    const float* obj = s_obj + env * 7;
+    const float* goal = s_goal + env * 7;
+    const float* tips = s_tips + env * 9;
+    const float* hist = s_hist + env * HS;
     if (live) {
-      const float ox = row[L::OFF_OBJ], oy = row[L::OFF_OBJ + 1], oz = row[L::OFF_OBJ + 2];
-      const float gx = row[L::OFF_GOAL], gy = row[L::OFF_GOAL + 1], gz = row[L::OFF_GOAL + 2];
-      const Quat gq{row[L::OFF_GOAL + 3], row[L::OFF_GOAL + 4], row[L::OFF_GOAL + 5], row[L::OFF_GOAL + 6]};
-      if (sub == 0) {
+      const float gx = goal[0], gy = goal[1], gz = goal[2];
+      if (rw == 0) {
         // finger_reach_object_rate (rewards.py:219-235): sum_i (|tip_i - obj| - |tip_i' - obj'|)
+        const float ox = obj[0], oy = obj[1], oz = obj[2];
         const float px = hist[9], py = hist[10], pz = hist[11];
         float acc = 0.0f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const float cur = norm3(tip_pos(env, i, 0) - ox, tip_pos(env, i, 1) - oy, tip_pos(env, i, 2) - oz);
+          const float cur = norm3(tips[3 * i] - ox, tips[3 * i + 1] - oy, tips[3 * i + 2] - oz);
           const float prev = norm3(hist[3 * i] - px, hist[3 * i + 1] - py, hist[3 * i + 2] - pz);
           acc = acc + (cur - prev);
         }
-        va = s_coef[C_REACH] * acc;
-      } else if (sub == 1) {
+        s_part[0][env] = s_coef[C_REACH] * acc;
+      } else if (rw == 1) {
         // finger_move_penalty (rewards.py:261-263): sum_9 ((tip - tip') / dt)^2
-        const float dt = s_coef[C_DT];
-        float acc = 0.0f;
+        const float dt = s_coef[C_DT], dt_rcp = s_coef[C_DT_RCP];
+        float acc = 0.0f, dmax = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float v = __fdiv_rn(tip_pos(env, i, c) - hist[3 * i + c], dt);
-            acc = acc + v * v;
+        for (int k = 0; k < 9; ++k) {
+          const float d = div_by_const(tips[k] - hist[k], dt, dt_rcp, dmax);
+          acc = acc + d * d;
+        }
+        if (!(dmax < kDivSafeMax)) {  // cold
+          acc = 0.0f;
+          for (int k = 0; k < 9; ++k) {
+            const float d = __fdiv_rn(tips[k] - hist[k], dt);
+            acc = acc + d * d;
           }
-        va = s_coef[C_MOVE] * acc;
+        }
+        s_part[1][env] = s_coef[C_MOVE] * acc;
         // object_dist (rewards.py:62-63) and object_move (rewards.py:88-91)
-        const float d = norm3(ox - gx, oy - gy, oz - gz);
+        const float d = norm3(obj[0] - gx, obj[1] - gy, obj[2] - gz);
         const float dprev = norm3(hist[9] - gx, hist[10] - gy, hist[11] - gz);
-        vb = lgsk(d, 50.0f) * s_coef[C_DIST];
-        vc = s_coef[C_OBJMOVE] * (d - dprev);
-        vd = d;
-      } else if (sub == 2) {
-        // object_rot (rewards.py:134-139): w * (gate*dt) / (scale*|theta| + scale)
-        const Quat oq{row[L::OFF_OBJ + 3], row[L::OFF_OBJ + 4], row[L::OFF_OBJ + 5], row[L::OFF_OBJ + 6]};
-        const float theta = quat_diff_rad(oq, gq);
-        const float den = s_coef[C_ROT_SCALE] * fabsf(theta) + s_coef[C_ROT_SCALE];
-        va = (__frcp_rn(den) * s_coef[C_ROT_SCHED]) * s_coef[C_ROT_W];
-        vb = theta;
+        s_part[2][env] = lgsk(d, 50.0f) * s_coef[C_DIST];
+        s_part[3][env] = s_coef[C_OBJMOVE] * (d - dprev);
+        s_part[4][env] = d;
       } else {
-        // previous-orientation angle for object_rot_delta (rewards.py:179)
-        const Quat pq{hist[12], hist[13], hist[14], hist[15]};
-        vb = fabsf(quat_diff_rad(pq, gq));
+        const Quat gq{goal[3], goal[4], goal[5], goal[6]};
+        if (rw == 2) {
+          // object_rot (rewards.py:134-139): w * (gate*dt) / (scale*|theta| + scale)
+          const Quat oq{obj[3], obj[4], obj[5], obj[6]};
+          const float theta = quat_diff_rad(oq, gq);
+          const float den = s_coef[C_ROT_SCALE] * fabsf(theta) + s_coef[C_ROT_SCALE];
+          s_part[5][env] = (__frcp_rn(den) * s_coef[C_ROT_SCHED]) * s_coef[C_ROT_W];
+          s_part[6][env] = theta;
+        } else {
+          // previous-orientation angle for object_rot_delta (rewards.py:179)
+          const Quat pq{hist[12], hist[13], hist[14], hist[15]};
+          s_part[7][env] = fabsf(quat_diff_rad(pq, gq));
+        }
       }
     }
-    // gather the sub-results onto lane sub==0 of each env
-    const unsigned full = 0xffffffffu;
-    const int base = (tid & 31) & ~3;
-    const float t_move = __shfl_sync(full, va, base + 1);
-    const float t_dist = __shfl_sync(full, vb, base + 1);
-    const float t_objmove = __shfl_sync(full, vc, base + 1);
-    const float dist = __shfl_sync(full, vd, base + 1);
-    const float t_rot = __shfl_sync(full, va, base + 2);
-    const float theta = __shfl_sync(full, vb, base + 2);
-    const float theta_prev_abs = __shfl_sync(full, vb, base + 3);
-
-    if (sub == 0) {
-      float st[LG_NUM_STATS];
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four reward warps
+  }
+  if (REWARD && rw == 0) {
+    // ---- warp 0: combine, terminate, count (one lane per env) -----------------------------------------
+    const int env = renv;
+    const bool live = renv < nvalid;
+    float st[LG_NUM_STATS];
 #pragma unroll
-      for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0f;
-      if (live) {
-        const float t_reach = va;
-        // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
-        const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - theta_prev_abs));
-        const float terms[6] = {t_reach, t_move, t_dist, t_rot, t_delta, t_objmove};
-        float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
+    for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0f;
+    if (live) {
+      const int64_t e = e0 + env;
+      const float dist = s_part[4][env], theta = s_part[6][env];
+      // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
+      const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - s_part[7][env]));
+      const float terms[6] = {s_part[0][env], s_part[1][env], s_part[2][env], s_part[5][env], t_delta, s_part[3][env]};
+      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          if (P.terms[k].activate) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = terms[k]; }
-          if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
-        }
-        // __check_termination (trifinger_env.py:1053-1099)
-        const bool pos_ok = dist <= s_coef[C_POS_TOL];
-        const bool rot_ok = theta <= s_coef[C_ROT_TOL];
-        bool done;
-        if (P.task_difficulty < 4) done = pos_ok;
-        else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
-        else done = rot_ok;
-        bool goal_reset = in_goal_reset != 0;
-        bool succ = in_succ != 0;
-        if (P.success_activate) {
-          if (done) reward = reward + s_coef[C_BONUS];
-          goal_reset = done;
-          succ = succ || goal_reset;
-          B.goal_reset[e] = goal_reset;
-        } else {
-          succ = goal_reset && succ;
-        }
-        B.successes[e] = succ;
-        B.reward[e] = reward;
-        // step counter, timeout, dones (envs/env_base.py:391-399)
-        bool reset = in_reset != 0;
-        if (P.fuse_bookkeeping) {
-          const int64_t steps = in_steps + 1;
-          B.steps_count[e] = steps;
-          if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
-          B.reset[e] = reset;
-        }
-        const bool dn = reset && goal_reset;
-        if (B.dones) B.dones[e] = dn;
-        st[LG_STAT_POSITION_GOAL] = pos_ok;
-        st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
-        st[LG_STAT_SUCCESSES] = succ;
-        st[LG_STAT_REWARD] = reward;
-        st[LG_STAT_RESETS] = reset;
-        st[LG_STAT_DONES] = dn;
+      for (int k = 0; k < 6; ++k) {
+        if ((P.term_active_mask >> k) & 1) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = terms[k]; }
+        if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
       }
-#pragma unroll
-      for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
+      // __check_termination (trifinger_env.py:1053-1099)
+      const bool pos_ok = dist <= s_coef[C_POS_TOL];
+      const bool rot_ok = theta <= s_coef[C_ROT_TOL];
+      bool done;
+      if (P.task_difficulty < 4) done = pos_ok;
+      else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
+      else done = rot_ok;
+      bool goal_reset = in_goal_reset != 0;
+      bool succ = in_succ != 0;
+      if (P.success_activate) {
+        if (done) reward = reward + s_coef[C_BONUS];
+        goal_reset = done;
+        succ = succ || goal_reset;
+        B.goal_reset[e] = goal_reset;
+      } else {
+        succ = goal_reset && succ;
+      }
+      B.successes[e] = succ;
+      B.reward[e] = reward;
+      // step counter, timeout, dones (envs/env_base.py:391-399)
+      bool reset = in_reset != 0;
+      if (P.fuse_bookkeeping) {
+        const int64_t steps = in_steps + 1;
+        B.steps_count[e] = steps;
+        if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
+        B.reset[e] = reset;
+      }
+      const bool dn = reset && goal_reset;
+      if (B.dones) B.dones[e] = dn;
+      st[LG_STAT_POSITION_GOAL] = pos_ok;
+      st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
+      st[LG_STAT_SUCCESSES] = succ;
+      st[LG_STAT_REWARD] = reward;
+      st[LG_STAT_RESETS] = reset;
+      st[LG_STAT_DONES] = dn;
     }
     // ---- episode statistics: per-CTA fp64 sums in a fixed order, one RED per slot, no fence ----------
-    asm volatile("bar.sync 1, %0;" :: "n"(NR) : "memory");  // the four reward warps only
-    if (tid <= LG_STAT_DONES) {
+#pragma unroll
+    for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
+    __syncwarp();
+    if (env <= LG_STAT_DONES) {
       double acc = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += (double)s_stat[tid][k];
+      for (int k = 0; k < E; ++k) acc += (double)s_stat[env][k];
       // reward-term, reward and success entries are means over this shard (trifinger_env.py:554, :1098),
       // the rest are counts (:1067, :1076)
-      const bool is_mean = tid < LG_STAT_POSITION_GOAL || tid == LG_STAT_SUCCESSES || tid == LG_STAT_REWARD;
+      const bool is_mean = env < LG_STAT_POSITION_GOAL || env == LG_STAT_SUCCESSES || env == LG_STAT_REWARD;
       if (is_mean) acc = acc / (double)P.num_envs;
-      atomicAdd(B.step_stats + tid, acc);
+      atomicAdd(B.step_stats + env, acc);
     }
   }
+  emit_outputs();
 }
 
 // history seeding (trifinger_env.py:619-628): both entries = initial simulator state
@@ -538,6 +627,14 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   r_act.load(action_in + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
   if (want_torque) r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
   if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
+  if (tile == 0 && tid == NT - 1 && P.use_device_clock) {
+    // device clock: advance the frame counter and publish the reward coefficients of the coming
+    // post-physics pass (env_steps_count = frames x global env count, envs/env_base.py:286-289);
+    // done by an otherwise idle lane while the tile's loads are in flight
+    const int64_t frame = B.control->frame_count + P.control_decimation;
+    B.control->frame_count = frame;
+    if (B.reward_coef) compute_coefs(P, (double)(frame * P.global_num_envs), B.reward_coef);
+  }
 
   // ---- block scan of both masks + aggregate publication (env_base.py:374-379) -------------------
   const bool f_reset = flag_r != 0, f_goal = flag_g != 0;
@@ -614,7 +711,6 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     B.goal_reset_ids[j] = e;
     if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
   }
-  if (tile == 0 && tid == 0 && P.use_device_clock) B.control->frame_count += P.control_decimation;
 }
 
 // standalone compaction (torch.nonzero(mask).view(-1))
@@ -734,16 +830,28 @@ __global__ void keypoints_kernel(const float* pose, float size, float* out, int6
   out[i * 3] = p[0] + rx; out[i * 3 + 1] = p[1] + ry; out[i * 3 + 2] = p[2] + rz;
 }
 
-// exhaustive check of div_by_const against IEEE division for one (span, rcp): all 2^32 numerators
-__global__ void selftest_division_kernel(float span, float rcp, unsigned long long* mismatches) {
+// exhaustive check of div_by_const's contract for one (span, rcp): all 2^32 numerators.
+// out[0] = in-window numerators that are not bit-identical to IEEE division (must be 0);
+// out[1] = worst ulp distance for 0 < |x| < 2^-100 (must be <= 1); out[2] = huge/inf numerators not flagged.
+__global__ void selftest_division_kernel(float span, float rcp, unsigned long long* out) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  unsigned long long bad = 0;
+  unsigned long long bad = 0, unflagged = 0;
+  unsigned int worst = 0;
   for (uint64_t bits = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bits < (1ull << 32); bits += stride) {
     const float x = __uint_as_float((uint32_t)bits);
-    const float a = div_by_const(x, span, rcp), b = __fdiv_rn(x, span);
-    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) ++bad;
+    float amax = 0.0f;
+    const float a = div_by_const(x, span, rcp, amax), b = __fdiv_rn(x, span);
+    const float ax = fabsf(x);
+    if (x != x) continue;                                   // nan in, nan out on both paths
+    if (!(ax < kDivSafeMax)) { if (amax < kDivSafeMax) ++unflagged; continue; }
+    if (ax == 0.0f) { if (a != 0.0f) ++bad; continue; }
+    if (ax >= 7.8886091e-31f /* 2^-100 */) { if (__float_as_uint(a) != __float_as_uint(b)) ++bad; continue; }
+    const int d = abs((int)(__float_as_uint(a) & 0x7fffffffu) - (int)(__float_as_uint(b) & 0x7fffffffu));
+    worst = max(worst, (unsigned int)d);
   }
-  if (bad) atomicAdd(mismatches, bad);
+  if (bad) atomicAdd(out, bad);
+  if (worst) atomicMax(out + 1, (unsigned long long)worst);
+  if (unflagged) atomicAdd(out + 2, unflagged);
 }
 
 }  // namespace lg
@@ -783,15 +891,26 @@ template <bool REWARD>
 int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, double sched, cudaStream_t st) {
   if (int rc = validate(P, S, B, true)) return rc;
   if (REWARD && !B->step_stats) return fail(LG_ERR_BAD_ARG, "null statistics buffer");
+  if (P->normalize_obs && !B->scale_table) return fail(LG_ERR_BAD_ARG, "null scale_table");
   if (REWARD && !P->fuse_bookkeeping) {
     // stand-alone _post_step: nobody zeroed the accumulators (lg_pre_physics does in the fused sequence)
     if (cudaMemsetAsync(B->step_stats, 0, LG_NUM_STATS * sizeof(double), st) != cudaSuccess) return check_launch("memset");
   }
   const int grid = (int)((P->num_envs + lg::kTileEnvs - 1) / lg::kTileEnvs);
   const bool asym = P->asymmetric_obs != 0;
-#define LG_LAUNCH(AD, AS) lg::post_physics_kernel<AD, AS, REWARD><<<grid, lg::kPostThreads, 0, st>>>(*P, *S, *B, sched)
-  if (P->action_dim == 9) { if (asym) LG_LAUNCH(9, true); else LG_LAUNCH(9, false); }
-  else { if (asym) LG_LAUNCH(18, true); else LG_LAUNCH(18, false); }
+  const bool clip = B->obs_clipped != nullptr;
+  if (clip && asym && !B->states_clipped) return fail(LG_ERR_BAD_ARG, "obs_clipped and states_clipped go together");
+  LgCoef cf;
+  std::memset(&cf, 0, sizeof(cf));
+  if (REWARD) {
+    if (P->use_device_clock) { if (!B->reward_coef) return fail(LG_ERR_BAD_ARG, "use_device_clock needs reward_coef"); }
+    else lg::compute_coefs(*P, sched, cf.v);
+  }
+#define LG_LAUNCH(AD, AS, CL) lg::post_physics_kernel<AD, AS, REWARD, CL><<<grid, lg::kPostThreads, 0, st>>>(*P, *S, *B, cf)
+#define LG_LAUNCH2(AD, AS) do { if (clip) LG_LAUNCH(AD, AS, true); else LG_LAUNCH(AD, AS, false); } while (0)
+  if (P->action_dim == 9) { if (asym) LG_LAUNCH2(9, true); else LG_LAUNCH2(9, false); }
+  else { if (asym) LG_LAUNCH2(18, true); else LG_LAUNCH2(18, false); }
+#undef LG_LAUNCH2
 #undef LG_LAUNCH
   return check_launch("post_physics_kernel");
 }

@@ -294,12 +294,17 @@ class TrifingerEnv(IsaacEnvBase):
         self._robot_indices = torch.zeros(N, **i32)
         self._reset_root_indices = torch.zeros(3 * N, **i32)
         self._goal_root_indices = torch.zeros(N, **i32)
+        self._reward_coef = torch.zeros(nat.LG_NUM_COEF, device=dev, dtype=torch.float)
         self._scan_status = torch.zeros(int(self._lib.lg_scan_tiles(N)), device=dev, dtype=torch.int64)
         self._control = torch.zeros(4, device=dev, dtype=torch.int64)  # LgControl, 32 bytes
         self._inject = {}
         self._P = build_params(self.config, N, env_offset=self._env_offset, global_num_envs=self._global_N,
                                fingertip_bodies=s.fingertip_bodies, bodies_per_env=s.bodies_per_env,
                                actors_per_env=s.actors_per_env, slots=s.slots)
+        tab = np.zeros((3, nat.LG_MAX_STATE_DIM), np.float32)
+        tab[0], tab[1], tab[2] = self._P.scale_centre, self._P.scale_span, self._P.scale_rcp
+        tab[1][tab[1] == 0] = 1.0
+        self._scale_table = torch.as_tensor(tab, device=dev).contiguous()
 
     def _configure_mdp_spaces(self):
         """Scale vectors as tensors, for callers that read them (ref trifinger_env.py:630-748)."""
@@ -337,6 +342,8 @@ class TrifingerEnv(IsaacEnvBase):
         b.reset_ids, b.goal_reset_ids, b.counts = p(self._reset_ids), p(self._goal_reset_ids), p(self._counts)
         b.robot_indices, b.reset_root_indices, b.goal_root_indices = p(self._robot_indices), p(self._reset_root_indices), p(self._goal_root_indices)
         b.scan_status, b.control = p(self._scan_status), p(self._control)
+        b.scale_table = p(self._scale_table)
+        b.reward_coef = p(self._reward_coef)
         self._B = b
         if not getattr(self, "_history_seeded", False):
             self._call("lg_init_history", self._P, self._S, self._B)  # ref trifinger_env.py:619-628

@@ -162,6 +162,7 @@ def build_params(cfg: dict, num_local_envs: int, env_offset: int = 0, global_num
     p.dof_pos_stddev = float(rd["robot_initial_state"].get("dof_pos_stddev", 0.0))
     p.dof_vel_stddev = float(rd["robot_initial_state"].get("dof_vel_stddev", 0.0))
     _fill_terms(p, cfg["reward_terms"])
+    p.term_active_mask = sum((1 << i) for i in range(nat.LG_NUM_TERMS) if p.terms[i].activate)
 
     lo, hi = state_scale(cfg) if cfg["asymmetric_obs"] else observation_scale(cfg)
     centre = ((lo + hi) * F(0.5)).astype(F)   # torch: (lower + upper) * 0.5 in fp32
