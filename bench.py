@@ -218,6 +218,15 @@ def run_gpu(args, wl):
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    if args.l2_fetch:
+        from leibnizgym_b200 import _native as nat
+        nat.check(nat.load().lg_set_l2_fetch_granularity(args.l2_fetch), "lg_set_l2_fetch_granularity")
+    if os.environ.get("LG_PDL_EARLY") == "0":
+        import ctypes
+        from leibnizgym_b200 import _native as nat
+        fn = nat.load().lg_debug_set_pdl_early
+        fn.argtypes, fn.restype = [ctypes.c_int], ctypes.c_int
+        assert fn(0) == 0
     N = wl["envs"]
     K, W = args.steps, max(args.warmup, 3)
     R = args.ring
@@ -387,6 +396,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity hint (32/64/128); 0 = leave")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:

@@ -214,6 +214,10 @@ const char* lg_last_error(void);
  * 3 LgControl, 4 LgRewardTerm, 5 LgHostStep */
 size_t lg_struct_size(int which);
 
+/* Hint for the device-wide L2 fetch granularity (cudaLimitMaxL2FetchGranularity): the path gathers 52-byte
+ * simulator rows, for which 32-byte fetches cut the DRAM over-fetch.  bytes in {32, 64, 128}. */
+int lg_set_l2_fetch_granularity(int bytes);
+
 /* number of look-back status words lg_pre_physics needs for n envs */
 int64_t lg_scan_tiles(int64_t num_envs);
 

@@ -99,6 +99,7 @@ SYMBOLS = {
     "lg_last_error": (C.c_char_p, []),
     "lg_struct_size": (C.c_size_t, [C.c_int]),
     "lg_scan_tiles": (_i64, [_i64]),
+    "lg_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "lg_pre_physics": (C.c_int, [_P, _S, _B, _vp, _vp]),
     "lg_post_physics": (C.c_int, [_P, _S, _B, C.c_double, _vp]),
     "lg_fill_observations": (C.c_int, [_P, _S, _B, _vp]),

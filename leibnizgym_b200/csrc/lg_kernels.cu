@@ -19,10 +19,17 @@
 
 namespace lg {
 
+// Programmatic dependent launch (PDL): a kernel launched with programmatic stream serialisation may
+// begin (CTA scheduling, parameter fetch, address set-up) before its predecessor has finished;
+// griddepcontrol.wait then blocks until the predecessor's grid has completed and its writes are
+// visible.  Two ~2 us launches per step make this worth ~1/4 of the step time at 16k envs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ int g_pdl_early = 1;
+__device__ __forceinline__ void pdl_launch_dependents() { if (g_pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =========================================================================================
 // post-physics: one CTA = one tile of E envs, 4 threads per env
 // =========================================================================================
-constexpr int kTileEnvs = 32;
 constexpr int kPostThreads = 256;
 
 template <int A, bool ASYM>
@@ -164,7 +171,7 @@ __device__ __noinline__ void output_exact(const LgParams& P, const LgBuffers& B,
 // Role order = output column order of the states row, except that the nine fingertip POSITION columns
 // come right after the observation columns: the lanes that feed obs, the reward staging and the next
 // history entry are then all in the first two warps of a part, and the other warps skip that code.
-template <int A, bool ASYM>
+template <int A, bool ASYM, int E>
 struct Roles {
   static constexpr int OBS = 32 + A;
   static constexpr int R_TIPPOS = OBS;                  // 9 roles
@@ -175,19 +182,18 @@ struct Roles {
   static constexpr int R_END = ASYM ? R_TQ + 9 : R_TIPREST;
   static constexpr int LANES = R_END <= 64 ? 64 : 128;  // role lanes per tile part
   static constexpr int PARTS = kPostThreads / LANES;    // the tile's envs are split over the parts
-  static constexpr int EP = kTileEnvs / PARTS;          // envs per lane
+  static constexpr int EP = E / PARTS;                  // envs per lane
+  static_assert(E % PARTS == 0 && E <= 32, "tile must split evenly; the reward math uses one lane per env");
   static constexpr int FRONT = R_TIPREST;               // roles < FRONT may feed obs / staging / history
   static_assert(R_END <= LANES, "more output columns than role lanes");
 };
 
-template <int A, bool ASYM, bool REWARD, bool CLIP>
+template <int A, bool ASYM, bool REWARD, bool CLIP, int E>
 __global__ void __launch_bounds__(kPostThreads, 4)
 post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                     const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
   using L = Layout<A, ASYM>;
-  using R = Roles<A, ASYM>;
-  constexpr int E = kTileEnvs;          // 32 envs per CTA
-  constexpr int NT = kPostThreads;      // 256 threads; after the barrier warps 0-3 do the reward math
+  using R = Roles<A, ASYM, E>;          // E envs per CTA
   constexpr int EP = R::EP;
   constexpr int HS = LG_HISTORY_COLS + 1;  // padded row: lane-per-env reads stay conflict free
   // only what the reward terms read is staged in shared memory (raw, unscaled)
@@ -261,6 +267,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     }
   }
   src += (e0 + env_first) * stride;
+  pdl_wait();  // everything above is independent of the previous kernel's results
   const int cnt = max(0, min(EP, nvalid - env_first));   // envs of this lane: env_first .. env_first + cnt - 1
   const bool full = nvalid == E;                           // every CTA but possibly the last
 
@@ -295,6 +302,8 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
     rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
   }
+
+  pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
 
   // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----
   if (REWARD && tid < C_COUNT) s_coef[tid] = P.use_device_clock ? __ldg(B.reward_coef + tid) : CF.v[tid];
@@ -472,8 +481,10 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       st[LG_STAT_DONES] = dn;
     }
     // ---- episode statistics: per-CTA fp64 sums in a fixed order, one RED per slot, no fence ----------
+    if (env < E) {  // lanes beyond the tile hold nothing (E < 32)
 #pragma unroll
-    for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
+      for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
+    }
     __syncwarp();
     if (env <= LG_STAT_DONES) {
       double acc = 0.0;
@@ -515,20 +526,24 @@ __device__ __forceinline__ bool status_valid(uint64_t w, uint32_t epoch) {
   return (uint32_t)(w >> 48) == (epoch & 0xffffu) && ((w >> 46) & 3u) != 0;
 }
 
-// Exclusive prefix of (a, b) over all tiles before `tile`; executed by the first warp of the CTA.
+// Exclusive prefix of (a, b) over all tiles before `tile`.  Block-wide: thread i inspects predecessor
+// tile-1-i (128 predecessors per round trip to L2), each warp reduces up to its nearest tile that
+// already holds an inclusive prefix, thread 0 chains the warps.  Called by every thread of the CTA.
 __device__ __forceinline__ void lookback(uint64_t* status, int tile, uint32_t epoch, uint32_t my_a, uint32_t my_b,
                                          uint32_t& ex_a, uint32_t& ex_b) {
-  const int lane = threadIdx.x & 31;
+  __shared__ uint32_t s_sum[kPreThreads / 32][2];
+  __shared__ int s_found[kPreThreads / 32];
+  __shared__ uint32_t s_res[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t acc_a = 0, acc_b = 0;
   int pos = tile - 1;
-  while (pos >= 0) {
-    const int idx = pos - lane;
+  bool done = tile == 0;
+  while (!done) {
+    const int idx = pos - (int)threadIdx.x;
     uint64_t w = 0;
-    bool ok;
-    do {
-      ok = true;
-      if (idx >= 0) { w = ld_volatile_u64(status + idx); ok = status_valid(w, epoch); }
-    } while (__any_sync(0xffffffffu, !ok));
+    if (idx >= 0) {
+      do { w = ld_volatile_u64(status + idx); } while (!status_valid(w, epoch));
+    }
     const bool incl = idx >= 0 && ((w >> 46) & 3u) == kStateInclusive;
     const unsigned incl_mask = __ballot_sync(0xffffffffu, incl);
     const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;  // nearest predecessor holding an inclusive prefix
@@ -536,15 +551,22 @@ __device__ __forceinline__ void lookback(uint64_t* status, int tile, uint32_t ep
     uint32_t b = (idx >= 0 && lane <= stop) ? (uint32_t)(w & 0x7fffffu) : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    acc_a += a; acc_b += b;
-    if (incl_mask) break;
-    pos -= 32;
+    if (lane == 0) { s_sum[warp][0] = a; s_sum[warp][1] = b; s_found[warp] = incl_mask != 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bool found = false;
+      for (int k = 0; k < kPreThreads / 32 && !found; ++k) { acc_a += s_sum[k][0]; acc_b += s_sum[k][1]; found = s_found[k] != 0; }
+      s_res[0] = acc_a; s_res[1] = acc_b; s_res[2] = found || pos - kPreThreads < 0;
+    }
+    __syncthreads();
+    done = s_res[2] != 0;
+    pos -= kPreThreads;
   }
-  ex_a = acc_a; ex_b = acc_b;
-  if (lane == 0) {
-    __threadfence();
-    atomicExch(reinterpret_cast<unsigned long long*>(status + tile),
-               (unsigned long long)pack_status(epoch, kStateInclusive, acc_a + my_a, acc_b + my_b));
+  if (threadIdx.x == 0) {
+    ex_a = acc_a; ex_b = acc_b;
+    if (tile > 0)
+      atomicExch(reinterpret_cast<unsigned long long*>(status + tile),
+                 (unsigned long long)pack_status(epoch, kStateInclusive, acc_a + my_a, acc_b + my_b));
   }
 }
 
@@ -560,17 +582,15 @@ template <bool TICKET>
 __device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* status, const TileScan& t, int num_tiles,
                                                  uint32_t& ex_a, uint32_t& ex_b, int32_t* counts_out) {
   __shared__ uint32_t s_ex[2];
-  if (threadIdx.x < 32) {
-    uint32_t a = 0, b = 0;
-    if (t.tile > 0) lookback(status, t.tile, t.epoch, t.total_a, t.total_b, a, b);
-    if (threadIdx.x == 0) {
-      s_ex[0] = a; s_ex[1] = b;
-      if (t.tile == num_tiles - 1) {
-        // every tile has read the epoch and taken its ticket by now (their aggregates are visible)
-        if (counts_out) { counts_out[0] = (int32_t)(a + t.total_a); counts_out[1] = (int32_t)(b + t.total_b); }
-        if (TICKET) { ctl->scan_ticket = 0; __threadfence(); }
-        ctl->scan_epoch = t.epoch + 1;
-      }
+  uint32_t a = 0, b = 0;
+  lookback(status, t.tile, t.epoch, t.total_a, t.total_b, a, b);
+  if (threadIdx.x == 0) {
+    s_ex[0] = a; s_ex[1] = b;
+    if (t.tile == num_tiles - 1) {
+      // every tile has read the epoch and taken its ticket by now (their aggregates are visible)
+      if (counts_out) { counts_out[0] = (int32_t)(a + t.total_a); counts_out[1] = (int32_t)(b + t.total_b); }
+      if (TICKET) { ctl->scan_ticket = 0; __threadfence(); }
+      ctl->scan_epoch = t.epoch + 1;
     }
   }
   __syncthreads();
@@ -605,6 +625,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   __shared__ int s_tile;
   __shared__ uint32_t s_wa[NT / 32], s_wb[NT / 32];
   const int tid = threadIdx.x;
+  pdl_wait();
   // every thread reads the epoch before the tile publishes anything, so the last tile may advance it
   const uint32_t epoch = ld_volatile_u32(&B.control->scan_epoch);
   int tile = blockIdx.x;
@@ -626,6 +647,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   ColSlab<18, E, NT> r_dof;
   r_act.load(action_in + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
   if (want_torque) r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
+  pdl_launch_dependents();
   if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
   if (tile == 0 && tid == NT - 1 && P.use_device_clock) {
     // device clock: advance the frame counter and publish the reward coefficients of the coming
@@ -637,18 +659,12 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   }
 
   // ---- block scan of both masks + aggregate publication (env_base.py:374-379) -------------------
+  // Needs only the two flag bytes, so it runs (and the tile's aggregate is visible to its successors)
+  // while the action / joint-state loads are still in flight; the look-back at the end then never waits.
   const bool f_reset = flag_r != 0, f_goal = flag_g != 0;
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned ba = __ballot_sync(0xffffffffu, f_reset), bb = __ballot_sync(0xffffffffu, f_goal);
   if (lane == 0) { s_wa[warp] = __popc(ba); s_wb[warp] = __popc(bb); }
-  // action store (envs/env_base.py:369) with the wrapper's clamp (wrappers/vec_task.py:162)
-  if (P.clip_input_actions) {
-    const float clip = P.clip_actions;
-#pragma unroll
-    for (int it = 0; it < r_act.ITERS; ++it) r_act.v[it] = fminf(fmaxf(r_act.v[it], -clip), clip);
-  }
-  r_act.drain(s_act + r_act.grp * A + r_act.col, A, nvalid);
-  if (want_torque) r_dof.drain(s_dof + r_dof.grp * 18 + r_dof.col, 18, nvalid);
   __syncthreads();
   TileScan t;
   t.tile = tile; t.epoch = epoch;
@@ -669,6 +685,15 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
                (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
   }
+  // action store (envs/env_base.py:369) with the wrapper's clamp (wrappers/vec_task.py:162)
+  if (P.clip_input_actions) {
+    const float clip = P.clip_actions;
+#pragma unroll
+    for (int it = 0; it < r_act.ITERS; ++it) r_act.v[it] = fminf(fmaxf(r_act.v[it], -clip), clip);
+  }
+  r_act.drain(s_act + r_act.grp * A + r_act.col, A, nvalid);
+  if (want_torque) r_dof.drain(s_dof + r_dof.grp * 18 + r_dof.col, 18, nvalid);
+  __syncthreads();
   uint32_t ex_a = 0, ex_b = 0;
   const bool need_rank_first = P.inject_draws != 0;  // injected draws are indexed by compaction rank
   if (need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
@@ -869,6 +894,51 @@ int check_launch(const char* what) {
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+bool env_flag(const char* name) { const char* v = std::getenv(name); return v && v[0] && v[0] != '0'; }
+int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; }
+
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+// bit 0: pre-physics kernel launched programmatically, bit 1: post-physics kernel.  Measured on B200 at
+// 16k envs: post only 12.7 us/step, none 13.1, both 14.1 — the pre kernel gains nothing from starting early.
+int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : env_int("LG_PDL", 2); return m; }
+
+// Launch with programmatic stream serialisation (PDL) unless LG_NO_PDL is set.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Envs per CTA of the post-physics kernel: 32 when the grid needs several waves anyway, otherwise the
+// smallest tile that still fits one wave (4 CTAs per SM) so that all SMs carry the same load.
+int pick_tile_envs(int64_t n) {
+  static const int forced = env_int("LG_TILE_ENVS", 0);
+  if (forced == 32 || forced == 28 || forced == 24 || forced == 16) return forced;
+  const int64_t capacity = (int64_t)sm_count() * 4;
+  if ((n + 31) / 32 > capacity) return 32;
+  const int cands[] = {16, 24, 28, 32};
+  for (int e : cands)
+    if ((n + e - 1) / e <= capacity) return e;
+  return 32;
+}
+
 int validate(const LgParams* P, const LgSimState* S, const LgBuffers* B, bool need_states) {
   if (!P || !S || !B) return fail(LG_ERR_BAD_ARG, "null LgParams / LgSimState / LgBuffers");
   if (P->num_envs <= 0) return fail(LG_ERR_BAD_ARG, "num_envs must be positive");
@@ -896,7 +966,6 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
     // stand-alone _post_step: nobody zeroed the accumulators (lg_pre_physics does in the fused sequence)
     if (cudaMemsetAsync(B->step_stats, 0, LG_NUM_STATS * sizeof(double), st) != cudaSuccess) return check_launch("memset");
   }
-  const int grid = (int)((P->num_envs + lg::kTileEnvs - 1) / lg::kTileEnvs);
   const bool asym = P->asymmetric_obs != 0;
   const bool clip = B->obs_clipped != nullptr;
   if (clip && asym && !B->states_clipped) return fail(LG_ERR_BAD_ARG, "obs_clipped and states_clipped go together");
@@ -906,12 +975,21 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
     if (P->use_device_clock) { if (!B->reward_coef) return fail(LG_ERR_BAD_ARG, "use_device_clock needs reward_coef"); }
     else lg::compute_coefs(*P, sched, cf.v);
   }
-#define LG_LAUNCH(AD, AS, CL) lg::post_physics_kernel<AD, AS, REWARD, CL><<<grid, lg::kPostThreads, 0, st>>>(*P, *S, *B, cf)
-#define LG_LAUNCH2(AD, AS) do { if (clip) LG_LAUNCH(AD, AS, true); else LG_LAUNCH(AD, AS, false); } while (0)
-  if (P->action_dim == 9) { if (asym) LG_LAUNCH2(9, true); else LG_LAUNCH2(9, false); }
-  else { if (asym) LG_LAUNCH2(18, true); else LG_LAUNCH2(18, false); }
-#undef LG_LAUNCH2
-#undef LG_LAUNCH
+  const int E = P->action_dim == 9 ? pick_tile_envs(P->num_envs) : 32;
+  const unsigned grid = (unsigned)((P->num_envs + E - 1) / E);
+  cudaError_t err;
+#define LG_K(AD, AS, CL, EE) launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE>, grid, lg::kPostThreads, st, *P, *S, *B, cf)
+#define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))
+  if (P->action_dim == 9) {
+    if (asym) err = clip ? LG_E(9, true, true) : LG_E(9, true, false);
+    else err = clip ? LG_E(9, false, true) : LG_E(9, false, false);
+  } else {
+    if (asym) err = clip ? LG_K(18, true, true, 32) : LG_K(18, true, false, 32);
+    else err = clip ? LG_K(18, false, true, 32) : LG_K(18, false, false, 32);
+  }
+#undef LG_E
+#undef LG_K
+  if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("post_physics_kernel: ") + cudaGetErrorString(err));
   return check_launch("post_physics_kernel");
 }
 }  // namespace
@@ -919,6 +997,12 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
 extern "C" {
 
 int lg_version(void) { return LG_VERSION; }
+int lg_debug_set_pdl_early(int on) { return cudaMemcpyToSymbol(lg::g_pdl_early, &on, sizeof(int)) == cudaSuccess ? LG_OK : check_launch("memcpyToSymbol"); }
+int lg_set_l2_fetch_granularity(int bytes) {
+  if (bytes != 32 && bytes != 64 && bytes != 128) return fail(LG_ERR_BAD_ARG, "granularity must be 32, 64 or 128");
+  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes) != cudaSuccess) return check_launch("cudaDeviceSetLimit");
+  return LG_OK;
+}
 const char* lg_last_error(void) { return g_error.c_str(); }
 size_t lg_struct_size(int which) {
   switch (which) {
@@ -958,9 +1042,11 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
   cudaStream_t st = (cudaStream_t)stream;
   // all tiles co-resident (<= 8 CTAs on each of 148 SMs): tiles are block indices; beyond that, tickets
   const bool ticket = tiles > 148 * 8;
-#define LG_PRE(AD, TK) lg::pre_physics_kernel<AD, TK><<<tiles, lg::kPreThreads, 0, st>>>(*P, *S, *B, action_in, tiles)
+cudaError_t err;
+#define LG_PRE(AD, TK) err = launch_pdl(pdl_mode() & 1, lg::pre_physics_kernel<AD, TK>, (unsigned)tiles, lg::kPreThreads, st, *P, *S, *B, action_in, tiles)
   if (P->action_dim == 9) { if (ticket) LG_PRE(9, true); else LG_PRE(9, false); }
   else { if (ticket) LG_PRE(18, true); else LG_PRE(18, false); }
+  if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("pre_physics_kernel: ") + cudaGetErrorString(err));
 #undef LG_PRE
   return check_launch("pre_physics_kernel");
 }
