@@ -455,23 +455,10 @@ class TrifingerEnv(IsaacEnvBase):
     def global_step_info(self) -> Dict[str, float]:
         """Whole-job statistics: all-reduces the 16 shard sums (the only cross-GPU traffic of the
         path) and divides by the global env count.  Synchronises the host."""
-        local_n = float(self.num_instances)
-        is_mean = torch.zeros(nat.LG_NUM_STATS, device=self._torch_device, dtype=torch.float64)
-        is_mean[:7] = 1.0
-        is_mean[nat.STAT_SUCCESSES] = is_mean[nat.STAT_REWARD] = 1.0
-        sums = self._step_stats * (is_mean * local_n + (1.0 - is_mean))  # means -> sums; counts stay
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        sums = sums.cpu().numpy()
-        out = {}
-        for i, name in enumerate(nat.TERM_NAMES[:6]):
-            if self.config["reward_terms"][name]["activate"]:
-                out[f"env/rewards/{name}"] = float(sums[i] / self._global_N)
-        out["env/current_position_goal/count"] = float(sums[nat.STAT_POSITION_GOAL])
-        out["env/current_orientation_goal/count"] = float(sums[nat.STAT_ORIENTATION_GOAL])
-        out["env/average_consecutive_success"] = float(sums[nat.STAT_SUCCESSES] / self._global_N)
-        return out
+        from .distributed import all_reduce_stats, stats_to_info
+        stats = all_reduce_stats(self._step_stats, self.num_instances, self._global_N)
+        active = [k for k, v in self.config["reward_terms"].items() if v["activate"]]
+        return stats_to_info(stats, active)
 
     # -- hooks, individually callable (ref trifinger_env.py:373-559, :959-994) ---------------------
     def _reset_impl(self, instances: torch.Tensor):

@@ -1,0 +1,232 @@
+"""GPU parity against the CPU oracle at BASELINE.json sizes, plus size-independent properties:
+sharding invariance, graph replay == eager, the wrapper's fused clipping, and the distribution of
+the kernel's own Philox stream (SURVEY.md §D option B: stated distributional check)."""
+import numpy as np
+import pytest
+import torch
+
+from tolerances import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(cfg, seq, N):
+    from leibnizgym_b200.config import resolve_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from oracle.trifinger_oracle import OracleEnv, OracleSim
+    env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    env.enable_term_rewards(True)
+    ora = OracleEnv(resolve_config(cfg), OracleSim(seq, N))
+    return env, ora
+
+
+def _check(key, got, exp, where):
+    ok, detail = compare(key, got.cpu().numpy() if torch.is_tensor(got) else got,
+                         exp.numpy() if torch.is_tensor(exp) else exp)
+    assert ok, (where, key, detail)
+
+
+@pytest.mark.parametrize("difficulty, N, reset_p", [(2, 16384, 0.0), (4, 16384, 0.3), (3, 65536, 0.05)])
+def test_full_size_steps_match_oracle(difficulty, N, reset_p):
+    """BASELINE.json configs 2, 5 and 3 at their real env counts, random draws injected on both sides."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.synthetic import bernoulli_masks, make_sequence
+    T = 4
+    cfg = difficulty_config(difficulty, N, asymmetric_obs=True, seed=5, episode_length=3)
+    seq = make_sequence(100 + difficulty, T, N)
+    masks = bernoulli_masks(7, T, N, reset_p)
+    env, ora = _pair(cfg, seq, N)
+    g = torch.Generator().manual_seed(3)
+    draws = lambda k: (torch.rand(k, 24, generator=g).numpy(), torch.randn(k, 8, generator=g).numpy())  # noqa: E731
+    d = draws(N)
+    env.inject_draws(reset=d)
+    ora.inject_draws(reset=d)
+    env.reset()
+    ora.reset()
+    for t in range(1, T):
+        if masks is not None:
+            ora.reset_buf |= masks[t]
+            env._reset_buf |= masks[t].cuda()
+        k = int(ora.reset_buf.sum())
+        d = draws(k) if k else None
+        env.inject_draws(reset=d)
+        ora.inject_draws(reset=d)
+        env.step(seq.action[t].cuda())
+        ora.step(seq.action[t].clone())
+        w = (difficulty, t)
+        _check("reset_ids", env.reset_env_ids, ora.last_ids[0], w)
+        _check("obs", env.obs_buf, ora.obs_buf, w)
+        _check("states", env.states_buf, ora.states_buf, w)
+        _check("terms", env._term_rewards[:6], ora.last_terms, w)
+        _check("reward", env.reward_buf, ora.reward_buf, w)
+        _check("reset_buf", env._reset_buf, ora.reset_buf, w)
+        _check("steps_count", env._steps_count_buf, ora.steps_count_buf, w)
+        _check("goal_pose", env._object_goal_poses_buf, ora.goal_poses, w)
+        _check("pre_sim_dof", env._dof_state, ora.sim.dof, w)
+        info = {k_: float(v) for k_, v in env._step_info.items()}
+        for k_, v in ora.step_info.items():
+            assert abs(info[k_] - float(v)) <= 1e-5 * abs(float(v)) + 2e-4, (w, k_, info[k_], float(v))
+
+
+def test_sharding_is_invisible():
+    """Two shards (contiguous halves of the global env range) reproduce the un-sharded run bit for bit,
+    including the kernel's own random stream (keyed by GLOBAL env id) and the schedule step."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import StateSequence, make_sequence
+    N, T = 4096, 5
+    cfg = difficulty_config(4, N, asymmetric_obs=True, seed=11, episode_length=2,
+                            reset_distribution={"robot_initial_state": {"type": "random", "dof_pos_stddev": 0.4,
+                                                                        "dof_vel_stddev": 0.2}})
+    cfg["reward_terms"]["finger_reach_object_rate"].update(thresh_sched_start=0, thresh_sched_end=3 * N)
+    seq = make_sequence(12, T, N)
+
+    def shard(first, last):
+        return StateSequence(seq.dof_state[:, first:last].contiguous(), seq.root_state[:, 4 * first:4 * last].contiguous(),
+                             seq.rigid_body[:, first:last].contiguous(), seq.dof_force[:, first:last].contiguous(),
+                             seq.ft_sensors[:, first:last].contiguous(), seq.action[:, first:last].contiguous())
+
+    def run(rank, world):
+        n = N // world
+        sq = shard(rank * n, (rank + 1) * n).to("cuda:0")
+        env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(sq, "cuda:0"), rank=rank, world_size=world)
+        env.reset()
+        outs = []
+        for t in range(1, T):
+            env.step(sq.action[t])
+            outs.append([x.clone() for x in (env.obs_buf, env.states_buf, env.reward_buf, env._reset_buf,
+                                             env._object_goal_poses_buf, env._dof_state)])
+        return outs
+
+    whole = run(0, 1)
+    halves = [run(0, 2), run(1, 2)]
+    for t in range(T - 1):
+        for i in range(6):
+            joined = torch.cat([halves[0][t][i], halves[1][t][i]], dim=0)
+            assert torch.equal(joined, whole[t][i]), (t, i)
+
+
+def test_graph_replay_equals_eager_steps():
+    """CUDA-graph replay with the device-side clock (frame counter, reward coefficients, RNG epoch in
+    device memory) gives the same buffers as eager host-clock stepping through the same states."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.graph_runner import GraphRunner
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    N, R = 2048, 4
+    cfg = difficulty_config(4, N, asymmetric_obs=True, seed=21, episode_length=3)
+    cfg["reward_terms"]["object_dist"].update(thresh_sched_start=0, thresh_sched_end=5 * N)  # gate flips inside the run
+    ring = make_sequence(22, R, N, device="cuda:0")
+
+    def fresh():
+        env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(ring, "cuda:0"))
+        env.reset()
+        return env
+
+    eager = fresh()
+    for t in range(2 * R):
+        eager.step(ring.action[eager._sim.cursor % R])
+    graph_env = fresh()
+    # the device clock starts where the host clock stands after reset()
+    graph_env._control[1] = graph_env._sim.get_frame_count()
+    runner = GraphRunner(graph_env, ring, rotate_outputs=False)
+    runner.t = graph_env._sim.cursor
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            for t in range(R):
+                runner._launch_step(runner.t + t, st)
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(runner.obs_slots[0], eager.obs_buf)
+    assert torch.equal(runner.state_slots[0], eager.states_buf)
+    assert torch.equal(graph_env.reward_buf, eager.reward_buf)
+    assert torch.equal(graph_env._steps_count_buf, eager._steps_count_buf)
+    assert torch.equal(graph_env._reset_buf, eager._reset_buf)
+    assert torch.equal(graph_env._history, eager._history)
+
+
+def test_vec_task_fused_clipping():
+    """VecTaskPython's three clamps (vec_task.py:146-170) come out of the fused kernels."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from leibnizgym_b200.wrappers import VecTaskPython
+    N = 1000  # ragged last tile
+    seq = make_sequence(31, 3, N)
+    seq.dof_state[:, :, :, 1] *= 20.0           # joint velocities far outside +-10 -> |obs| > 5 after scaling
+    env = TrifingerEnv(difficulty_config(4, N, seed=1), device="cuda:0", verbose=False,
+                       sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    vec = VecTaskPython(env, rl_device="cuda:0", clip_obs=5.0, clip_actions=1.0)
+    assert (vec.num_envs, vec.num_obs, vec.num_states, vec.num_actions) == (N, 41, 113, 9)
+    vec.reset()
+    act = 3.0 * seq.action[1].cuda()
+    obs, rew, done, info = vec.step(act)
+    assert torch.equal(obs, torch.clamp(env.obs_buf, -5.0, 5.0)) and float(obs.abs().max()) == 5.0
+    assert torch.equal(vec.get_state(), torch.clamp(env.states_buf, -5.0, 5.0))
+    assert torch.equal(env.action_buf, torch.clamp(act, -1.0, 1.0))
+    assert obs.data_ptr() != env.obs_buf.data_ptr() and rew.shape == (N,) and done.dtype == torch.bool
+    with pytest.raises(ValueError):
+        vec.step(act[:, :8])
+
+
+def test_own_random_stream_distributions():
+    """The samplers on the kernel's Philox stream: r^2/R^2, theta, z uniform; goal quaternion uniform on S^3
+    (components^2 ~ Beta(1/2, 3/2)); joint noise uniform; deterministic in (seed, epoch, env)."""
+    from scipy import stats
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    N = 200_000
+    cfg = difficulty_config(4, N, asymmetric_obs=False, seed=77,
+                            reset_distribution={"robot_initial_state": {"type": "random", "dof_pos_stddev": 0.4,
+                                                                        "dof_vel_stddev": 0.2}})
+    seq = make_sequence(1, 1, N, device="cuda:0")
+
+    def sample(seed):
+        c = dict(cfg, seed=seed)
+        env = TrifingerEnv(c, device="cuda:0", verbose=False, sim=SyntheticSim(seq, "cuda:0"))
+        env._reset_impl(torch.arange(N, device="cuda:0"))
+        torch.cuda.synchronize()
+        return (env._object_goal_poses_buf.cpu().numpy().astype(np.float64), env._dof_state.cpu().numpy().astype(np.float64),
+                env._actors_root_state.view(N, 4, 13)[:, 2].cpu().numpy().astype(np.float64), env)
+
+    goal, dof, obj, env = sample(77)
+    R = 0.195 - 0.065 * np.sqrt(3) / 2
+    ks = lambda x, cdf: stats.kstest(x, cdf).pvalue  # noqa: E731
+    r2 = (goal[:, 0] ** 2 + goal[:, 1] ** 2) / R ** 2
+    assert r2.max() <= 1.0 + 1e-6 and ks(r2, "uniform") > 1e-3
+    theta = np.mod(np.arctan2(goal[:, 1], goal[:, 0]), 2 * np.pi) / (2 * np.pi)
+    assert ks(theta, "uniform") > 1e-3
+    z = (goal[:, 2] - 0.065 * np.sqrt(3) / 2) / (0.1 - 0.065 * np.sqrt(3) / 2)
+    assert z.min() >= -1e-6 and z.max() <= 1 + 1e-6 and ks(z, "uniform") > 1e-3
+    q = goal[:, 3:7]
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-6
+    for c in range(4):
+        assert ks(q[:, c] ** 2, stats.beta(0.5, 1.5).cdf) > 1e-3, c
+    assert abs(np.corrcoef(q[:, 0], q[:, 1])[0, 1]) < 0.01 and abs(np.corrcoef(goal[:-1, 0], goal[1:, 0])[0, 1]) < 0.01
+    # object: disc + yaw; robot: default + std * U(-1, 1)
+    r2o = (obj[:, 0] ** 2 + obj[:, 1] ** 2) / R ** 2
+    assert ks(r2o, "uniform") > 1e-3 and np.allclose(obj[:, 2], 0.0325)
+    yaw = np.mod(2 * np.arctan2(obj[:, 5], obj[:, 6]), 2 * np.pi) / (2 * np.pi)
+    assert ks(yaw, "uniform") > 1e-3
+    default = np.array([0.0, 0.9, -1.7] * 3)
+    u = (dof[:, :, 0] - default) / 0.4
+    assert np.abs(u).max() <= 1 + 1e-6 and ks((u[:, 4] + 1) / 2, "uniform") > 1e-3
+    assert ks((dof[:, 7, 1] / 0.2 + 1) / 2, "uniform") > 1e-3
+    assert abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.01
+    # determinism and seed sensitivity
+    goal2, _, _, _ = sample(77)
+    goal3, _, _, _ = sample(78)
+    assert np.array_equal(goal, goal2) and not np.array_equal(goal, goal3)
+    # a second reset call draws fresh numbers (the epoch advanced)
+    env._reset_impl(torch.arange(N, device="cuda:0"))
+    assert not np.array_equal(goal, env._object_goal_poses_buf.cpu().numpy().astype(np.float64))
