@@ -9,7 +9,9 @@ different HBM lines and nothing is served from L2 by accident of the benchmark.
 
 Schedule step and RNG epoch come from the device-side LgControl block
 (`use_device_clock`), so a replayed graph still advances `env_steps_count` and draws
-fresh random numbers.
+fresh random numbers.  Resets write their rows into the ring slot the simulator would
+consume next, so a ring that wraps around replays slightly different states on later
+passes (harmless for timing; tests compare like with like).
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ from .synthetic import StateSequence
 
 class GraphRunner:
     def __init__(self, env: TrifingerEnv, ring: StateSequence, rotate_outputs: bool = True,
-                 inject_reset_masks: Optional[torch.Tensor] = None):
+                 inject_reset_masks: Optional[torch.Tensor] = None, device_clock: bool = True):
         assert ring.dof_state.is_cuda, "the ring must be device resident"
         self.env, self.ring = env, ring
         self.R = ring.num_steps
@@ -36,8 +38,12 @@ class GraphRunner:
         self.state_slots = torch.zeros((self.R if rotate_outputs else 1, N, sd), device=dev) if sd else None
         self.reset_masks = inject_reset_masks  # [R, N] bool or None: OR-ed into _reset_buf before each step
         self.P = nat.LgParams.from_buffer_copy(env._P)
-        self.P.use_device_clock = 1
+        self.P.use_device_clock = int(device_clock)
         self.P.fuse_bookkeeping = 1
+        self.device_clock = device_clock
+        self.frame0 = env._sim.get_frame_count()   # host clock: frames before the runner's first step
+        if device_clock:
+            env._control[1] = self.frame0           # LgControl.frame_count
         self._S: List[nat.LgSimState] = []
         self._B: List[nat.LgBuffers] = []
         for t in range(self.R):
@@ -54,7 +60,8 @@ class GraphRunner:
             self._B.append(b)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.steps_per_graph = 0
-        self.t = 0  # ring cursor of the next eager step
+        self.t = 0   # ring cursor of the next eager step
+        self.t0 = 0  # ring cursor of the runner's first step (host clock only)
 
     # -- one step, eager (also what gets captured) -----------------------------------------
     def _launch_step(self, t: int, stream: int, post_only: bool = False) -> None:
@@ -66,7 +73,8 @@ class GraphRunner:
             # resets write into the tensors the simulator consumes next (slot of the previous state)
             nat.check(self.lib.lg_pre_physics(self.P, self._S[prev], self._B[prev],
                                               self.ring.action[s].data_ptr(), stream), "lg_pre_physics")
-        nat.check(self.lib.lg_post_physics(self.P, self._S[s], self._B[s], 0.0, stream), "lg_post_physics")
+        sched = 0.0 if self.device_clock else float((self.frame0 + (t - self.t0) + 1) * self.env._global_N)
+        nat.check(self.lib.lg_post_physics(self.P, self._S[s], self._B[s], sched, stream), "lg_post_physics")
 
     def step_eager(self, n: int = 1, post_only: bool = False) -> None:
         stream = torch.cuda.current_stream().cuda_stream

@@ -21,10 +21,26 @@ def _pair(cfg, seq, N):
     return env, ora
 
 
-def _check(key, got, exp, where):
+def _check(key, got, exp, where, extra=None):
     ok, detail = compare(key, got.cpu().numpy() if torch.is_tensor(got) else got,
-                         exp.numpy() if torch.is_tensor(exp) else exp)
+                         exp.numpy() if torch.is_tensor(exp) else exp, extra_atol=extra)
     assert ok, (where, key, detail)
+
+
+def _angle_allowance(ora):
+    """Conditioning-aware slack of the two angle-derived terms and of the reward (tolerances.angle_slack)."""
+    from tolerances import angle_slack
+    cur = angle_slack(ora.obj_hist[0][:, 3:7], ora.goal_poses[:, 3:7])
+    prev = angle_slack(ora.obj_hist[1][:, 3:7], ora.goal_poses[:, 3:7])
+    t = ora.terms
+    rot = abs(t["object_rot"]["weight"]) * 0.02 / t["object_rot"]["scale"] * cur      # |d term / d theta| <= w dt / scale
+    delta = abs(t["object_rot_delta"]["weight"]) * (cur + prev)
+    terms = np.zeros((6, len(cur)))
+    terms[3], terms[4] = rot, delta
+    reward = rot * t["object_rot"]["activate"] + delta * t["object_rot_delta"]["activate"]
+    frac_ill = float(np.mean((cur > 1e-4) | (prev > 1e-4)))
+    assert frac_ill < 0.03, frac_ill   # a material slack only for the ~1 % of pairs within ~0.01 rad of pi
+    return terms, reward
 
 
 @pytest.mark.parametrize("difficulty, N, reset_p", [(2, 16384, 0.0), (4, 16384, 0.3), (3, 65536, 0.05)])
@@ -58,8 +74,9 @@ def test_full_size_steps_match_oracle(difficulty, N, reset_p):
         _check("reset_ids", env.reset_env_ids, ora.last_ids[0], w)
         _check("obs", env.obs_buf, ora.obs_buf, w)
         _check("states", env.states_buf, ora.states_buf, w)
-        _check("terms", env._term_rewards[:6], ora.last_terms, w)
-        _check("reward", env.reward_buf, ora.reward_buf, w)
+        slack_terms, slack_reward = _angle_allowance(ora)
+        _check("terms", env._term_rewards[:6], ora.last_terms, w, slack_terms)
+        _check("reward", env.reward_buf, ora.reward_buf, w, slack_reward)
         _check("reset_buf", env._reset_buf, ora.reset_buf, w)
         _check("steps_count", env._steps_count_buf, ora.steps_count_buf, w)
         _check("goal_pose", env._object_goal_poses_buf, ora.goal_poses, w)
@@ -110,7 +127,7 @@ def test_sharding_is_invisible():
 
 def test_graph_replay_equals_eager_steps():
     """CUDA-graph replay with the device-side clock (frame counter, reward coefficients, RNG epoch in
-    device memory) gives the same buffers as eager host-clock stepping through the same states."""
+    device memory) gives the same buffers as eager launches driven by the host clock."""
     from leibnizgym_b200.config import difficulty_config
     from leibnizgym_b200.env import TrifingerEnv
     from leibnizgym_b200.graph_runner import GraphRunner
@@ -119,21 +136,18 @@ def test_graph_replay_equals_eager_steps():
     N, R = 2048, 4
     cfg = difficulty_config(4, N, asymmetric_obs=True, seed=21, episode_length=3)
     cfg["reward_terms"]["object_dist"].update(thresh_sched_start=0, thresh_sched_end=5 * N)  # gate flips inside the run
-    ring = make_sequence(22, R, N, device="cuda:0")
 
-    def fresh():
+    def fresh(device_clock):
+        ring = make_sequence(22, R, N, device="cuda:0")   # own copy: resets write into the ring
         env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(ring, "cuda:0"))
         env.reset()
-        return env
+        runner = GraphRunner(env, ring, rotate_outputs=False, device_clock=device_clock)
+        runner.t = runner.t0 = env._sim.cursor
+        return env, runner
 
-    eager = fresh()
-    for t in range(2 * R):
-        eager.step(ring.action[eager._sim.cursor % R])
-    graph_env = fresh()
-    # the device clock starts where the host clock stands after reset()
-    graph_env._control[1] = graph_env._sim.get_frame_count()
-    runner = GraphRunner(graph_env, ring, rotate_outputs=False)
-    runner.t = graph_env._sim.cursor
+    eager_env, eager = fresh(False)
+    eager.step_eager(2 * R)
+    graph_env, runner = fresh(True)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         g = torch.cuda.CUDAGraph()
@@ -144,12 +158,14 @@ def test_graph_replay_equals_eager_steps():
         g.replay()
         g.replay()
     torch.cuda.synchronize()
-    assert torch.equal(runner.obs_slots[0], eager.obs_buf)
-    assert torch.equal(runner.state_slots[0], eager.states_buf)
-    assert torch.equal(graph_env.reward_buf, eager.reward_buf)
-    assert torch.equal(graph_env._steps_count_buf, eager._steps_count_buf)
-    assert torch.equal(graph_env._reset_buf, eager._reset_buf)
-    assert torch.equal(graph_env._history, eager._history)
+    assert torch.equal(runner.obs_slots[0], eager.obs_slots[0])
+    assert torch.equal(runner.state_slots[0], eager.state_slots[0])
+    assert torch.equal(graph_env.reward_buf, eager_env.reward_buf)
+    assert torch.equal(graph_env._steps_count_buf, eager_env._steps_count_buf)
+    assert torch.equal(graph_env._reset_buf, eager_env._reset_buf)
+    assert torch.equal(graph_env._history, eager_env._history)
+    assert torch.equal(graph_env._object_goal_poses_buf, eager_env._object_goal_poses_buf)  # same RNG epochs
+    assert float(eager_env.reward_buf.abs().sum()) > 0
 
 
 def test_vec_task_fused_clipping():

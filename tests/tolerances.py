@@ -22,8 +22,21 @@ ATOL = {
 }
 
 
-def compare(key, got, expected):
-    """Returns (ok, detail)."""
+def angle_slack(q_a, q_b):
+    """Per-env allowance (radians) for theta = 2 asin(min(|v|, 1)) (utils/torch_utils.py:145-150).
+    d(theta)/d|v| = 2 / sqrt(1 - |v|^2) is unbounded as theta -> pi: one ulp of |v| (which a different
+    but equally valid fp32 evaluation order of the 2-norm, or of the sampled goal quaternion's
+    normalisation, legitimately produces) moves theta by up to ~7e-4 rad there.  The allowance is
+    2 ulp of |v| through that slope; it is ~5e-7 rad for well-conditioned pairs."""
+    import torch
+    from oracle.trifinger_oracle import quat_conjugate, quat_mul
+    v = quat_mul(torch.as_tensor(q_a), quat_conjugate(torch.as_tensor(q_b)))[:, :3].double().norm(dim=-1).clamp(max=1.0)
+    eps = 2.0 ** -23
+    return (2.0 * 2.0 * eps / torch.sqrt(torch.clamp(1.0 - v * v, min=2.0 * eps))).numpy()
+
+
+def compare(key, got, expected, extra_atol=None):
+    """Returns (ok, detail).  `extra_atol` (broadcastable) adds a data-dependent absolute allowance."""
     got, expected = np.asarray(got), np.asarray(expected)
     if got.shape != expected.shape:
         return False, f"shape {got.shape} != {expected.shape}"
@@ -33,6 +46,8 @@ def compare(key, got, expected):
     g, x = got.astype(np.float64), expected.astype(np.float64)
     err = np.abs(g - x)
     bound = ATOL[key] + RTOL * np.abs(x)
+    if extra_atol is not None:
+        bound = bound + np.asarray(extra_atol, dtype=np.float64)
     bad = ~((err <= bound) | (np.isnan(g) & np.isnan(x)))
     if bad.any():
         i = np.unravel_index(np.argmax(np.where(bad, err, 0)), err.shape)
