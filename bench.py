@@ -63,6 +63,18 @@ PRE_BYTES = 2 + 36 + 36 + 72 + 36          # flags, action in, action out, dof_s
 RESET_BYTES = 300                           # extra per resetting env
 
 
+def measured_traffic(envs: int, asym: bool):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["post_physics_kernel"]
+        if t["workload_envs"] == envs and bool(t["asymmetric"]) == bool(asym):
+            return t["bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -311,7 +323,7 @@ def run_gpu(args, wl):
                                 f"({ring.nbytes() / 2**20:.0f} MiB) and {R} output slots per GPU",
                    "steps_per_graph": C, "reset_fraction_per_step": wl["reset_p"]},
         "roofline": {"bound": "hbm", "kernel": "post_physics_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N, asym), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,
                      "whole_step_gbs": step_bytes / (step_ms_total / K * 1e-3) / 1e9},
         "clocks": clocks,
