@@ -166,6 +166,8 @@ def time_cpu_path(wl: dict, envs: int, steps: int, warmup: int, max_seconds: flo
             super().simulate()
             TimedSim.sim_seconds += time.perf_counter() - t0
 
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(int(os.environ.get("LG_CPU_THREADS", os.cpu_count() or 1)))
     cfg = resolve_config(difficulty_config(wl["difficulty"], envs, asymmetric_obs=wl["asym"], seed=wl["seed"]))
     T = 4
     seq = make_sequence(wl["seed"], T, envs)
@@ -328,7 +330,7 @@ def run_gpu(args, wl):
                      "whole_step_gbs": step_bytes / (step_ms_total / K * 1e-3) / 1e9},
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": 2 * K,
+        "gpu_launches": 2 * K * world,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         r = time_cpu_path(wl, N, steps=10_000, warmup=3, max_seconds=args.cpu_seconds)
@@ -344,34 +346,50 @@ def run_gpu(args, wl):
 
 
 def run_e2e(args, wl, cfg, dev, rank, world):
-    """Public-API step with HOST-resident simulator state: every step uploads the five simulator
-    tensors + the action from pinned memory and downloads obs, states, reward, dones."""
+    """Public-API step (VecTaskPython.step + get_state) with HOST-resident simulator state, action and
+    results, every step.  Three transports (--e2e-mode):
+      zc      (default) zero copy: the simulator tensors and the action sit in pinned host memory and the
+              fused kernels read the rows they need — and write obs/states/reward/dones — over PCIe themselves;
+      zc_out  inputs staged by host->device copies of the five simulator tensors, results written to the host
+              by the kernels;
+      copy    (default) inputs staged by host->device copies (of the rigid-body tensor only the run of bodies
+              that holds the fingertips), results copied back with four device->host copies."""
     import torch.distributed as dist
 
     from leibnizgym_b200.env import TrifingerEnv
-    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.sim import HostZeroCopySim, SyntheticSim
     from leibnizgym_b200.wrappers import VecTaskPython
 
     N = wl["envs"]
     T = 4
-    host = make_sequence(wl["seed"], T, N, first_env=rank * N).to("cpu", pin=True)
-    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(host, dev), rank=rank, world_size=world)
-    vec = VecTaskPython(env, rl_device=dev, clip_obs=5.0, clip_actions=1.0)
-    vec.reset()
+    mode = args.e2e_mode
     asym = wl["asym"]
-    pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()  # noqa: E731
-    h_obs, h_rew, h_done = pin(N, env.get_obs_dim()), pin(N), pin(N, dt=torch.bool)
-    h_states = pin(N, env.get_state_dim()) if asym else None
+    host = make_sequence(wl["seed"], T, N, first_env=rank * N).to("cpu", pin=True)
+    sim = HostZeroCopySim(host) if mode == "zc" else SyntheticSim(host, dev)
+    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=sim, rank=rank, world_size=world)
+    if mode != "zc" and not args.e2e_full_upload:
+        sim.use_sparse_upload(env._P)
+    vec = VecTaskPython(env, rl_device=dev if mode == "copy" else "cpu", clip_obs=5.0, clip_actions=1.0)
+    vec.reset()
+    obs_dim, st_dim = env.get_obs_dim(), env.get_state_dim()
+    if mode == "copy":
+        pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()  # noqa: E731
+        h_obs, h_rew, h_done = pin(N, obs_dim), pin(N), pin(N, dt=torch.bool)
+        h_states = pin(N, st_dim) if asym else None
     steps = max(8, min(args.e2e_steps, args.steps))
+    sink = torch.zeros(1)
 
     def one(t):
-        obs, rew, done, _ = vec.step(host.action[t % T])   # host action -> device inside step()
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
-        if asym:
-            h_states.copy_(vec.get_state(), non_blocking=True)
+        obs, rew, done, _ = vec.step(host.action[t % T])   # pinned host action
+        states = vec.get_state() if asym else None
+        if mode == "copy":
+            h_obs.copy_(obs, non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_done.copy_(done, non_blocking=True)
+            if asym:
+                h_states.copy_(states, non_blocking=True)
         torch.cuda.synchronize()                           # the caller consumes the results every step
+        return obs if mode != "copy" else h_obs
 
     for t in range(3):
         one(t)
@@ -381,19 +399,24 @@ def run_e2e(args, wl, cfg, dev, rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(steps):
-        one(t)
+        o = one(t)
     e1.record()
     torch.cuda.synchronize()
+    sink += float(o[0, 0])                                 # the host really reads the result
     ms = e0.elapsed_time(e1)
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    h2d = 4 * N * (18 + 4 * 13 + 20 * 13 + 9 + 18 + 9)
-    d2h = 4 * N * (env.get_obs_dim() + env.get_state_dim() + 1) + N
-    return {"value": steps * N * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "steps": steps, "ms_per_step": ms / steps,
-            "api": "VecTaskPython.step + get_state, pinned host simulator state"}
+    bodies = 20 if args.e2e_full_upload else 11   # rigid bodies staged per env (fingertips are bodies 6, 11, 16)
+    full_h2d = 4 * N * (18 + 4 * 13 + bodies * 13 + 9 + 18 + 9)
+    # zero copy: bytes the kernels fetch from host memory = the rows the path reads (dof_state twice: torque + obs)
+    zc_h2d = 4 * N * (9 + 18 + 18 + 13 + 39 + (9 + 18 if asym else 0))
+    d2h = 4 * N * (obs_dim + st_dim + 1 + (0 if mode == "copy" else 9)) + N   # zero-copy modes also return the torque
+    return {"value": steps * N * world / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": zc_h2d if mode == "zc" else full_h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": ms / steps, "mode": mode,
+            "api": "VecTaskPython.step + get_state; simulator state, action and results in pinned host memory"}
 
 
 def main():
@@ -406,6 +429,8 @@ def main():
     ap.add_argument("--envs", type=int, default=None, help="override envs per GPU")
     ap.add_argument("--ring", type=int, default=32, help="distinct simulator states in HBM")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-mode", default="copy", choices=["zc", "zc_out", "copy"])
+    ap.add_argument("--e2e-full-upload", action="store_true", help="upload all 20 rigid bodies, not just the fingertip run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity hint (32/64/128); 0 = leave")

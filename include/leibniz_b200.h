@@ -298,6 +298,10 @@ typedef struct LgHostStep {
   float* obs_host; float* states_host; float* reward_host; uint8_t* dones_host;
   float* action_staging;    /* device [N, A] scratch for the uploaded action */
 } LgHostStep;
+/* Host -> device staging of one simulator state (pinned host pointers of H; outputs of H unused): the whole
+ * dof_state / root_state / dof_force / ft_sensors tensors, and of rigid_body only the contiguous run of bodies
+ * that contains the three fingertips (one strided 2-D copy; 11 of 20 bodies for the TriFinger). */
+int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep* H, void* stream);
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B,
                  const LgHostStep* H, double sched_step, void* stream);
 

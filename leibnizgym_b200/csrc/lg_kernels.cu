@@ -1127,6 +1127,27 @@ int lg_selftest_division(float span, float rcp, unsigned long long* mismatches_d
   return check_launch("selftest_division_kernel");
 }
 
+int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep* H, void* stream) {
+  if (!P || !S || !H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host)
+    return fail(LG_ERR_BAD_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = P->num_envs;
+  const cudaMemcpyKind k = cudaMemcpyHostToDevice;
+  cudaMemcpyAsync(S->dof_state, H->dof_state_host, sizeof(float) * N * 18, k, st);
+  cudaMemcpyAsync(S->root_state, H->root_state_host, sizeof(float) * N * P->actors_per_env * 13, k, st);
+  // rigid bodies: only the contiguous run of bodies that contains the three fingertips (bodies 6..16 of 20)
+  int lo = P->fingertip_body[0], hi = P->fingertip_body[0];
+  for (int i = 1; i < 3; ++i) { lo = P->fingertip_body[i] < lo ? P->fingertip_body[i] : lo; hi = P->fingertip_body[i] > hi ? P->fingertip_body[i] : hi; }
+  const size_t pitch = sizeof(float) * 13 * P->bodies_per_env, width = sizeof(float) * 13 * (hi - lo + 1);
+  cudaMemcpy2DAsync(const_cast<float*>(S->rigid_body) + lo * 13, pitch, H->rigid_body_host + lo * 13, pitch, width, (size_t)N, k, st);
+  if (P->asymmetric_obs) {
+    if (!H->dof_force_host || !H->ft_sensors_host) return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
+    cudaMemcpyAsync(const_cast<float*>(S->dof_force), H->dof_force_host, sizeof(float) * N * 9, k, st);
+    cudaMemcpyAsync(const_cast<float*>(S->ft_sensors), H->ft_sensors_host, sizeof(float) * N * 18, k, st);
+  }
+  return check_launch("lg_upload_sim_state");
+}
+
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {
   if (int rc = validate(P, S, B, true)) return rc;
   if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||
@@ -1138,15 +1159,8 @@ int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, con
   // the action arrives first: the pre-physics pass (resets, torque) consumes it together with last step's state
   cudaMemcpyAsync(H->action_staging, H->action_host, sizeof(float) * N * P->action_dim, cudaMemcpyHostToDevice, st);
   if (int rc = lg_pre_physics(P, S, B, H->action_staging, stream)) return rc;
-  // "physics": the simulator's new state lands in the device tensors
-  cudaMemcpyAsync(S->dof_state, H->dof_state_host, sizeof(float) * N * 18, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(S->root_state, H->root_state_host, sizeof(float) * N * P->actors_per_env * 13, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(const_cast<float*>(S->rigid_body), H->rigid_body_host, sizeof(float) * N * P->bodies_per_env * 13, cudaMemcpyHostToDevice, st);
-  if (P->asymmetric_obs) {
-    if (!H->dof_force_host || !H->ft_sensors_host || !H->states_host) return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
-    cudaMemcpyAsync(const_cast<float*>(S->dof_force), H->dof_force_host, sizeof(float) * N * 9, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(const_cast<float*>(S->ft_sensors), H->ft_sensors_host, sizeof(float) * N * 18, cudaMemcpyHostToDevice, st);
-  }
+  // "physics": the simulator's new state lands in the device tensors (only the rows the path reads)
+  if (int rc = lg_upload_sim_state(P, S, H, stream)) return rc;
   if (int rc = lg_post_physics(P, S, B, sched_step, stream)) return rc;
   const float* obs_src = B->obs_clipped ? B->obs_clipped : B->obs;
   cudaMemcpyAsync(H->obs_host, obs_src, sizeof(float) * N * obs_dim, cudaMemcpyDeviceToHost, st);

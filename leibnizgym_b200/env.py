@@ -160,6 +160,9 @@ class IsaacEnvBase:
         shape = (self.num_instances, self.get_action_dim())
         if tuple(action.size()) != shape:
             raise ValueError(f"Invalid shape for tensor `action`. Input: {tuple(action.size())} != {shape}.")
+        if getattr(self, "_host_io", False) and action.device.type == "cpu" and action.is_pinned() \
+                and action.dtype == torch.float and action.is_contiguous():
+            return action  # pinned host memory is addressable from the kernel (UVA): no staging copy
         return action.to(self._torch_device, dtype=torch.float, non_blocking=True).contiguous()
 
     def step(self, action: Union[np.ndarray, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
@@ -375,6 +378,28 @@ class TrifingerEnv(IsaacEnvBase):
             self._P.clip_actions, self._P.clip_input_actions = float(clip_actions), 1
         self._bind()
 
+    def enable_host_outputs(self, clip_obs: Optional[float] = None, clip_actions: Optional[float] = None):
+        """Zero-copy result path for a HOST-side learner or simulator: the fused kernels store what the
+        caller reads every step — (clipped) obs and states, reward, dones, applied torque — straight into
+        pinned host memory over PCIe, as part of the same pass, instead of a device buffer plus a
+        device-to-host copy.  The returned tensors are then pinned CPU tensors, valid once the stream is
+        synchronised.  Un-clipped obs/states stay device resident when clipping is on."""
+        pin = lambda t: torch.zeros(t.shape, dtype=t.dtype).pin_memory()  # noqa: E731
+        if clip_obs is not None:
+            self._P.clip_obs = float(clip_obs)
+            self._obs_clipped = pin(self._obs_buf)
+            self._states_clipped = pin(self._states_buf) if self.config["asymmetric_obs"] else None
+        else:
+            self._obs_buf = pin(self._obs_buf)
+            self._states_buf = pin(self._states_buf)
+        if clip_actions is not None:
+            self._P.clip_actions, self._P.clip_input_actions = float(clip_actions), 1
+        self._reward_buf = pin(self._reward_buf)
+        self._dones = pin(self._dones)
+        self._applied_torque = pin(self._applied_torque)
+        self._host_io = True
+        self._bind()
+
     def inject_draws(self, reset=None, goal=None):
         """Test hook: the next reset / goal reset reads these (uniforms [k,24], normals [k,8])
         instead of the Philox stream; rows are indexed by ascending-id rank."""
@@ -415,6 +440,13 @@ class TrifingerEnv(IsaacEnvBase):
 
     def _simulate(self):
         self._sim.simulate()
+        if getattr(self._sim, "rebinds_tensors", False):  # zero-copy simulators hand out a new set of tensors
+            s, p = self._sim, nat.ptr
+            self._S = nat.LgSimState(p(s.dof_state), p(s.root_state), p(s.rigid_body), p(s.dof_force), p(s.ft_sensors))
+            N = self.num_instances
+            self._dof_state = s.dof_state.view(N, 9, 2)
+            self._rigid_body_state = s.rigid_body.view(N, s.bodies_per_env, 13)
+            self._actors_root_state = s.root_state.view(-1, 13)
 
     @property
     def reset_env_ids(self) -> torch.Tensor:

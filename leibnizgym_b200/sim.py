@@ -39,16 +39,40 @@ class SyntheticSim:
         self.slots = (0, 2, 3)  # robot, object, goal actor slots inside one env
         self.before_simulate: Optional[Callable[["SyntheticSim"], None]] = None  # test hook
         self.applied_torque = None
+        self._uploader = None
         self._load(0)  # what refresh_* shows before the first simulate
 
     def _load(self, t: int) -> None:
         s = self.seq
+        if self._uploader is not None:   # pinned host sequence: stage only the rows the path reads
+            self._uploader(t)
+            return
         nb = s.dof_state.device.type == "cpu"
         self.dof_state.copy_(s.dof_state[t], non_blocking=nb)
         self.root_state.copy_(s.root_state[t], non_blocking=nb)
         self.rigid_body.copy_(s.rigid_body[t], non_blocking=nb)
         self.dof_force.copy_(s.dof_force[t], non_blocking=nb)
         self.ft_sensors.copy_(s.ft_sensors[t], non_blocking=nb)
+
+    def use_sparse_upload(self, params) -> None:
+        """Host-resident sequences: stage each state with lg_upload_sim_state (whole small tensors, and of the
+        rigid-body tensor only the run of bodies holding the fingertips) instead of five full copies."""
+        from . import _native as nat
+        if self.seq.dof_state.device.type != "cpu" or not self.seq.dof_state.is_pinned():
+            return
+        lib = nat.load()
+        S = nat.LgSimState(*(x.data_ptr() for x in (self.dof_state, self.root_state, self.rigid_body,
+                                                     self.dof_force, self.ft_sensors)))
+
+        def upload(t):
+            s = self.seq
+            H = nat.LgHostStep()
+            H.dof_state_host, H.root_state_host = s.dof_state[t].data_ptr(), s.root_state[t].data_ptr()
+            H.rigid_body_host = s.rigid_body[t].data_ptr()
+            H.dof_force_host, H.ft_sensors_host = s.dof_force[t].data_ptr(), s.ft_sensors[t].data_ptr()
+            nat.check(lib.lg_upload_sim_state(params, S, H, torch.cuda.current_stream(self.device).cuda_stream),
+                      "lg_upload_sim_state")
+        self._uploader = upload
 
     # -- the slice of the gym API the path uses ---------------------------------------
     def simulate(self) -> None:
@@ -69,3 +93,51 @@ class SyntheticSim:
 
     def set_actor_root_state_tensor_indexed(self, indices: torch.Tensor, count) -> None:
         """As above for `root_state`."""
+
+
+class HostZeroCopySim:
+    """Simulator whose state lives in pinned HOST memory and is read by the kernels in place.
+
+    The situation of the reference's default CPU pipeline (`use_gpu_pipeline: False`, ref
+    envs/env_base.py:60): PhysX keeps its tensors on the host.  Instead of staging them through a
+    device copy every step, the env kernels read the rows they need (and write reset rows) directly
+    over PCIe — pinned memory is device-addressable under UVA.  `simulate()` makes the next state of
+    the sequence current by swapping tensor references (`rebinds_tensors`), which is what a host
+    simulator that double-buffers its output would do; nothing is copied on the host either.
+    """
+
+    rebinds_tensors = True
+
+    def __init__(self, seq: StateSequence):
+        assert seq.dof_state.device.type == "cpu" and seq.dof_state.is_pinned(), "needs a pinned host sequence"
+        self.seq = seq
+        self.num_envs = seq.num_envs
+        self.frame_count = 0
+        self.cursor = 0
+        self.fingertip_bodies = (6, 11, 16)
+        self.bodies_per_env, self.actors_per_env = 20, 4
+        self.slots = (0, 2, 3)
+        self.applied_torque = None
+        self._select(0)
+
+    def _select(self, t: int) -> None:
+        s = self.seq
+        self.dof_state, self.root_state, self.rigid_body = s.dof_state[t], s.root_state[t], s.rigid_body[t]
+        self.dof_force, self.ft_sensors = s.dof_force[t], s.ft_sensors[t]
+
+    def simulate(self) -> None:
+        self._select(self.cursor % self.seq.num_steps)
+        self.cursor += 1
+        self.frame_count += 1
+
+    def get_frame_count(self) -> int:
+        return self.frame_count
+
+    def set_dof_actuation_force_tensor(self, torque: torch.Tensor) -> None:
+        self.applied_torque = torque
+
+    def set_dof_state_tensor_indexed(self, indices, count) -> None:
+        pass
+
+    def set_actor_root_state_tensor_indexed(self, indices, count) -> None:
+        pass

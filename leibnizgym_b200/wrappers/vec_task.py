@@ -98,7 +98,11 @@ class VecTaskPython(VecTask):
         super().__init__(task, rl_device, clip_obs, clip_actions)
         self._fused = hasattr(task, "enable_clipped_outputs")
         if self._fused:
-            task.enable_clipped_outputs(self._clip_obs, self._clip_actions)
+            if torch.device(rl_device).type == "cpu" and hasattr(task, "enable_host_outputs"):
+                # host-side learner: the clipped results are stored straight into pinned host memory
+                task.enable_host_outputs(self._clip_obs, self._clip_actions)
+            else:
+                task.enable_clipped_outputs(self._clip_obs, self._clip_actions)
 
     def get_state(self) -> torch.Tensor:
         if self._fused and self._task._states_clipped is not None:
