@@ -61,7 +61,7 @@ enum LgResetKind { LG_RESET_NONE = 0, LG_RESET_DEFAULT = 1, LG_RESET_RANDOM = 2 
 /* slots of the statistics vector (sums over the envs of this shard; the reference's
  * `_step_info` means are sum / num_envs — trifinger_env.py:554, :1067-1068, :1076, :1098-1099) */
 enum LgStat {
-  LG_STAT_TERM0 = 0,            /* .. LG_STAT_TERM0 + 6: per-term reward sums          */
+  LG_STAT_TERM0 = 0,            /* .. LG_STAT_TERM0 + 6: per-term reward means (6 = keypoint extension) */
   LG_STAT_POSITION_GOAL = 7,    /* count of envs within the position tolerance         */
   LG_STAT_ORIENTATION_GOAL = 8, /* count of envs within the orientation tolerance      */
   LG_STAT_SUCCESSES = 9,        /* count of set `_successes` flags                     */
@@ -199,8 +199,8 @@ typedef struct LgBuffers {
   LgControl* control;
   float* reward_coef;       /* [LG_NUM_COEF] device copy of LgCoef, written by lg_pre_physics when
                                P.use_device_clock (optional otherwise)                              */
-  const float* scale_table; /* [3, LG_MAX_STATE_DIM] device copy of P.scale_centre | scale_span | scale_rcp
-                               (coalesced reads; the parameter block is a constant bank)             */
+  const float* scale_table; /* [4, LG_MAX_STATE_DIM] device copy of P.scale_centre | scale_span | scale_rcp |
+                               dr_sigma (coalesced reads; the parameter block is a constant bank)    */
   /* test hook (P.inject_draws): canonical draw arrays indexed by compaction rank */
   const float* inject_reset_u;  /* [k, 24] robot noise 0:18 | object r,theta,yaw | goal u0,u1,u2 */
   const float* inject_reset_n;  /* [k, 8]  goal quaternion 0:4 | ang-vel axis 4:7 | magnitude 7  */

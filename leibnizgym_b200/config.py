@@ -98,16 +98,15 @@ def default_trifinger_config() -> Dict[str, Any]:
         # ---- the default path is the reference's; SURVEY.md §8c "parity unpinned")
         "domain_randomization": {
             "activate": False,
-            "obs_noise_std": {  # additive Gaussian on RAW channels, before scale_transform
-                "robot_q": 0.0, "robot_u": 0.0, "object_q": 0.0, "object_q_des": 0.0,
-                "command": 0.0, "object_u": 0.0, "fingertip_state": 0.0, "robot_a": 0.0,
-                "fingertip_wrench": 0.0,
-            },
+            # additive Gaussian on the RAW actor observation groups, before scale_transform (the TODO of
+            # trifinger_env.py:979); the critic's states stay clean
+            "obs_noise_std": {"robot_q": 0.0, "robot_u": 0.0, "object_q": 0.0, "object_q_des": 0.0, "command": 0.0},
             "action_noise_std": 0.0,  # additive Gaussian on the action before clipping
         },
     }
 
 
+# extension reward term (no reference code); add as reward_terms["keypoint"] to enable
 KEYPOINT_TERM_DEFAULT = {"activate": False, "weight": 2000, "scale": 30.0, "eps": 2.0}
 
 

@@ -90,6 +90,15 @@ __device__ __forceinline__ float quat_diff_rad(const Quat a, const Quat b) {  //
   return 2.0f * asinf(quat_diff_sine(a, b));
 }
 
+// extension: the 8 cube corners (+-s/2)^3 rotated by the pose quaternion and translated
+__device__ __forceinline__ void quat_rotate(const Quat q, float vx, float vy, float vz, float& ox, float& oy, float& oz) {
+  // v' = v + 2 w (q_v x v) + 2 q_v x (q_v x v)
+  const float tx = 2.0f * (q.y * vz - q.z * vy), ty = 2.0f * (q.z * vx - q.x * vz), tz = 2.0f * (q.x * vy - q.y * vx);
+  ox = vx + q.w * tx + (q.y * tz - q.z * ty);
+  oy = vy + q.w * ty + (q.z * tx - q.x * tz);
+  oz = vz + q.w * tz + (q.x * ty - q.y * tx);
+}
+
 // 2 * (x - centre) / span with centre = (lo + hi) * 0.5, span = hi - lo (torch_utils.py:33-36)
 __device__ __forceinline__ float scale_transform(float x, float centre, float span) {
   return __fdiv_rn(2.0f * (x - centre), span);
@@ -158,6 +167,16 @@ struct DrawSource {
     const uint32_t w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
     return u01(w);
   }
+  // canonical uniform columns 4b .. 4b+3 with ONE Philox evaluation
+  __device__ __forceinline__ void uniform4(int b, float out[4]) const {
+    if (inj_u) {
+      const float* p = inj_u + 4 * b;
+      out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3];
+      return;
+    }
+    const U4 r = block((uint32_t)b);
+    out[0] = u01(r.x); out[1] = u01(r.y); out[2] = u01(r.z); out[3] = u01(r.w);
+  }
   // four normals: cols 0..3 (first = true) or 4..7
   __device__ __forceinline__ void normal4(bool first, float out[4]) const {
     if (inj_n) {
@@ -211,22 +230,23 @@ __device__ __forceinline__ Quat sample_orientation(const float n[4]) {
 }
 
 // __sample_object_goal_poses (envs/trifinger/trifinger_env.py:1194-1265; draw order SURVEY.md §A.5)
-__device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource& dr, float pose[7], float angvel[3]) {
+__device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource& dr, const float ug[3], float pose[7],
+                                            float angvel[3]) {
   const int d = P.task_difficulty;
   float x = 0.0f, y = 0.0f, z;
   Quat q{0.0f, 0.0f, 0.0f, 1.0f};
   const float half = (float)P.cube_half_size;
   if (d == -1 || d == 1 || d == 3 || d == 4 || d == 5)
-    sample_disc(dr.uniform(21), dr.uniform(22), (float)P.max_com_distance, x, y);
+    sample_disc(ug[0], ug[1], (float)P.max_com_distance, x, y);
   if (d == -1) {
     z = half;
-    q = sample_yaw(dr.uniform(23));
+    q = sample_yaw(ug[2]);
   } else if (d == 1) {
     z = half;
   } else if (d == 3) {
-    z = (float)(P.cube_max_height - P.cube_half_size) * dr.uniform(23) + half;
+    z = (float)(P.cube_max_height - P.cube_half_size) * ug[2] + half;
   } else if (d == 4 || d == 5) {
-    z = (float)(P.cube_max_height - P.cube_radius_3d) * dr.uniform(23) + (float)P.cube_radius_3d;
+    z = (float)(P.cube_max_height - P.cube_radius_3d) * ug[2] + (float)P.cube_radius_3d;
   } else {  // 2, 6: fixed position in the air
     z = (float)(P.cube_half_size + 0.05);
   }
@@ -252,9 +272,11 @@ __device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource&
 // Writes the sampled goal into the goal buffers and the goal actor's root row
 // (trifinger_env.py:1248-1265).
 __device__ __forceinline__ void apply_goal_sample(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                                  int64_t e, const DrawSource& dr) {
-  float pose[7], angvel[3];
-  sample_goal(P, dr, pose, angvel);
+                                                  int64_t e, const DrawSource& dr, const float* ub5 = nullptr) {
+  float pose[7], angvel[3], u5[4];
+  if (ub5) { u5[1] = ub5[1]; u5[2] = ub5[2]; u5[3] = ub5[3]; }
+  else dr.uniform4(5, u5);                      // goal columns 21..23 live in uniform block 5
+  sample_goal(P, dr, u5 + 1, pose, angvel);
   float* gp = B.goal_pose + e * 7;
   float* gm = B.goal_movement + e * 6;
   float* row = S.root_state + ((int64_t)P.actors_per_env * e + P.goal_slot) * 13;
@@ -277,12 +299,17 @@ __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimStat
   //    is a dead write in the reference and has no counterpart here
   if (P.robot_reset != LG_RESET_NONE) {
     float* dof = S.dof_state + e * 18;
+    float un[20];
+    if (P.robot_reset == LG_RESET_RANDOM) {
+#pragma unroll
+      for (int b = 0; b < 5; ++b) dr.uniform4(b, un + 4 * b);   // columns 0..17: one Philox block per 4
+    }
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       float pos = P.dof_default_pos[j], vel = P.dof_default_vel[j];
       if (P.robot_reset == LG_RESET_RANDOM) {
-        const float np_ = 2.0f * dr.uniform(j) - 1.0f;
-        const float nv_ = 2.0f * dr.uniform(9 + j) - 1.0f;
+        const float np_ = 2.0f * un[j] - 1.0f;
+        const float nv_ = 2.0f * un[9 + j] - 1.0f;
         pos = pos + (float)P.dof_pos_stddev * np_;
         vel = vel + (float)P.dof_vel_stddev * nv_;
       }
@@ -292,13 +319,17 @@ __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimStat
   }
   // C) object pose (:1164-1192): history entry 0 gets (pose, 0 velocity); its pose part is what
   //    the next post-physics pass reads as "previous object pose" 
+  float ub5[4];
+  dr.uniform4(5, ub5);                           // column 20 (object yaw) and the goal columns 21..23
   if (P.object_reset != LG_RESET_NONE) {
     float x = 0.0f, y = 0.0f;
     const float z = (float)P.cube_half_size;
     Quat q{0.0f, 0.0f, 0.0f, 1.0f};
     if (P.object_reset == LG_RESET_RANDOM) {
-      sample_disc(dr.uniform(18), dr.uniform(19), (float)P.max_com_distance, x, y);
-      q = sample_yaw(dr.uniform(20));
+      float ub4[4];
+      dr.uniform4(4, ub4);                       // columns 18, 19 (disc radius, angle) are lanes 2, 3
+      sample_disc(ub4[2], ub4[3], (float)P.max_com_distance, x, y);
+      q = sample_yaw(ub5[0]);
     }
     const float pose[7] = {x, y, z, q.x, q.y, q.z, q.w};
     float* h = B.history + e * LG_HISTORY_COLS + 9;
@@ -309,7 +340,7 @@ __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimStat
     for (int c = 7; c < 13; ++c) row[c] = 0.0f;
   }
   // D) goal (:408-411)
-  apply_goal_sample(P, S, B, e, dr);
+  apply_goal_sample(P, S, B, e, dr, ub5);
 }
 
 // _pre_step for ONE env (trifinger_env.py:442-498): action -> applied joint torque

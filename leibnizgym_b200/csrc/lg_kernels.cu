@@ -43,7 +43,8 @@ struct Layout {
 
 // coefficient slots computed once per CTA (python-float arithmetic of the reward modules)
 enum Coef { C_REACH = 0, C_MOVE, C_DIST, C_ROT_SCALE, C_ROT_SCHED, C_ROT_W, C_DELTA_RAMP, C_DELTA_W,
-            C_OBJMOVE, C_DT, C_DT_RCP, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_COUNT };
+            C_OBJMOVE, C_DT, C_DT_RCP, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_NOISE_EPOCH,
+            C_COUNT };
 
 __host__ __device__ inline double sched_gate(const LgRewardTerm& t, double T) {  // rewards.py:56-60
   if (t.sched_start != t.sched_end) return (t.sched_start <= T && T <= t.sched_end) ? 1.0 : 0.0;
@@ -77,6 +78,10 @@ __host__ __device__ inline void compute_coefs(const LgParams& P, double T, float
   c[C_KP_W] = (float)(t[6].weight * P.dt);
   c[C_KP_SCALE] = (float)t[6].scale;
   c[C_KP_EPS] = (float)t[6].eps;
+  // step identifier of the domain-randomisation noise stream: env_steps_count itself (bit pattern, not a value)
+  union { uint32_t u; float f; } bits;
+  bits.u = (uint32_t)(unsigned long long)T;
+  c[C_NOISE_EPOCH] = bits.f;
 }
 static_assert(C_COUNT <= LG_NUM_COEF, "LgCoef too small");
 
@@ -188,7 +193,7 @@ struct Roles {
   static_assert(R_END <= LANES, "more output columns than role lanes");
 };
 
-template <int A, bool ASYM, bool REWARD, bool CLIP, int E>
+template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT>
 __global__ void __launch_bounds__(kPostThreads, 4)
 post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                     const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
@@ -202,7 +207,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   __shared__ float s_tips[E * 9];       // fingertip positions
   __shared__ float s_hist[E * HS];      // previous fingertip positions (9) + previous object pose (7)
   __shared__ float s_coef[C_COUNT];
-  __shared__ float s_part[8][E];        // sub-task results of the reward warps
+  __shared__ float s_part[9][E];        // sub-task results of the reward warps
   __shared__ float s_stat[LG_NUM_STATS][E + 1];
 
   const int tid = threadIdx.x;
@@ -306,7 +311,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
 
   // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----
-  if (REWARD && tid < C_COUNT) s_coef[tid] = P.use_device_clock ? __ldg(B.reward_coef + tid) : CF.v[tid];
+  if (tid < C_COUNT) s_coef[tid] = (REWARD && P.use_device_clock) ? __ldg(B.reward_coef + tid) : CF.v[tid];
 
   // ---- phase 2: stage what the reward terms read, then ONE barrier -------------------------------
   // Only the warps that hold staged columns wait for (a small part of) their data here; the others
@@ -318,46 +323,63 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   }
   if (front && stage) {
     float* dst = stage + env_first * stage_stride;
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < EP; ++k)
-      if (full || k < cnt) dst[k * stage_stride] = v[k];
+      for (int k = 0; k < EP; ++k) dst[k * stage_stride] = v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (k < cnt) dst[k * stage_stride] = v[k];
+    }
   }
   __syncthreads();
 
   // ---- phase 3 (all warps; the reward warps come back to it after their math) -------------------------
-  auto emit_outputs = [&]() {
+  auto emit_outputs = [&](auto full_c) {
+    constexpr bool FULLC = decltype(full_c)::value;  // full tile: no per-element bound checks at all
     // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step.
     // After the barrier: every read of the previous entry has completed.
     if (front && hist_col >= 0) {
       float* dst = B.history + (e0 + env_first) * LG_HISTORY_COLS + hist_col;
 #pragma unroll
       for (int k = 0; k < EP; ++k)
-        if (full || k < cnt) dst[k * LG_HISTORY_COLS] = v[k];
+        if (FULLC || k < cnt) dst[k * LG_HISTORY_COLS] = v[k];
     }
     float amax = 0.0f;  // largest numerator seen: beyond 2^100 (never, for physical data) the column is redone exactly
     const float clip = P.clip_obs;
     const int st_off = env_first * L::STATE + dcol, ob_off = env_first * L::OBS + dcol;
     float* st = ASYM ? B.states + e0 * L::STATE + st_off : nullptr;                          // trifinger_env.py:990-994
     float* stc = (CLIP && ASYM) ? B.states_clipped + e0 * L::STATE + st_off : nullptr;       // vec_task.py:147
+    const bool to_obs = front && dcol >= 0 && dcol < L::OBS;
+    float* ob = B.obs + e0 * L::OBS + ob_off;                                                // trifinger_env.py:983-987
+    float* obc = CLIP ? B.obs_clipped + e0 * L::OBS + ob_off : nullptr;                      // vec_task.py:167
+    // extension (no reference code; the TODO at trifinger_env.py:979): additive Gaussian noise on the RAW
+    // actor observation, before scale_transform; the critic's states stay clean.  sigma = 0 -> skipped.
+    const float sigma = (EXT && P.dr_activate && to_obs) ? __ldg(B.scale_table + 3 * LG_MAX_STATE_DIM + dcol) : 0.0f;
+    const bool noisy = EXT && __any_sync(0xffffffffu, sigma != 0.0f);
 #pragma unroll
-    for (int k = 0; k < EP; ++k) v[k] = div_by_const(v[k] - centre, half_span, rcp_half, amax);
-    if (ASYM) {
-#pragma unroll
-      for (int k = 0; k < EP; ++k)
-        if (full || k < cnt) {
-          st[k * L::STATE] = v[k];
-          if (CLIP) stc[k * L::STATE] = fminf(fmaxf(v[k], -clip), clip);
+    for (int k = 0; k < EP; ++k) {
+      const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
+      if (FULLC || k < cnt) {
+        if (ASYM) {
+          st[k * L::STATE] = sv;
+          if (CLIP) stc[k * L::STATE] = fminf(fmaxf(sv, -clip), clip);
         }
-    }
-    if (front && dcol >= 0 && dcol < L::OBS) {
-      float* ob = B.obs + e0 * L::OBS + ob_off;                                              // trifinger_env.py:983-987
-      float* obc = CLIP ? B.obs_clipped + e0 * L::OBS + ob_off : nullptr;                    // vec_task.py:167
-#pragma unroll
-      for (int k = 0; k < EP; ++k)
-        if (full || k < cnt) {
-          ob[k * L::OBS] = v[k];
-          if (CLIP) obc[k * L::OBS] = fminf(fmaxf(v[k], -clip), clip);
+        if (to_obs) {
+          float ov = sv;
+          if (noisy) {
+            const uint64_t genv = (uint64_t)(P.env_offset + e0 + env_first + k);
+            const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, (uint32_t)dcol,
+                                          __float_as_uint(s_coef[C_NOISE_EPOCH])},
+                                       (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+            float n0, n1;
+            box_muller(r.x, r.y, n0, n1);
+            ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
+          }
+          ob[k * L::OBS] = ov;
+          if (CLIP) obc[k * L::OBS] = fminf(fmaxf(ov, -clip), clip);
         }
+      }
     }
     if (dcol >= 0 && !(amax < kDivSafeMax))  // cold: same addresses, same thread: plain overwrite
       output_exact<L::STATE, L::OBS, ASYM>(P, B, src, stride, cnt, e0 + env_first, dcol);
@@ -420,6 +442,23 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
           // previous-orientation angle for object_rot_delta (rewards.py:179)
           const Quat pq{hist[12], hist[13], hist[14], hist[15]};
           s_part[7][env] = fabsf(quat_diff_rad(pq, gq));
+          // extension (no reference code): keypoint pose reward
+          //   w dt mean_k lgsk(|kp_k - kp_k^goal|; scale, eps), kp_k = p + R(q) c_k over the 8 cube corners
+          if (EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1)) {
+            const Quat oq{obj[3], obj[4], obj[5], obj[6]};
+            const float h = (float)P.cube_half_size;
+            float acc = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const float cx = (kk & 1) ? h : -h, cy = (kk & 2) ? h : -h, cz = (kk & 4) ? h : -h;
+              float ax, ay, az, bx, by, bz;
+              quat_rotate(oq, cx, cy, cz, ax, ay, az);
+              quat_rotate(gq, cx, cy, cz, bx, by, bz);
+              const float dd = norm3((obj[0] + ax) - (gx + bx), (obj[1] + ay) - (gy + by), (obj[2] + az) - (gz + bz));
+              acc = acc + lgsk(dd, s_coef[C_KP_SCALE], s_coef[C_KP_EPS]);
+            }
+            s_part[8][env] = s_coef[C_KP_W] * (acc * 0.125f);
+          }
         }
       }
     }
@@ -437,10 +476,12 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       const float dist = s_part[4][env], theta = s_part[6][env];
       // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
       const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - s_part[7][env]));
-      const float terms[6] = {s_part[0][env], s_part[1][env], s_part[2][env], s_part[5][env], t_delta, s_part[3][env]};
-      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order
+      const bool kp_on = EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1);
+      const float terms[7] = {s_part[0][env], s_part[1][env], s_part[2][env], s_part[5][env], t_delta, s_part[3][env],
+                              kp_on ? s_part[8][env] : 0.0f};
+      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order (the extension term last)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
+      for (int k = 0; k < 7; ++k) {
         if ((P.term_active_mask >> k) & 1) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = terms[k]; }
         if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
       }
@@ -487,17 +528,24 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     }
     __syncwarp();
     if (env <= LG_STAT_DONES) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < E; ++k) acc += (double)s_stat[env][k];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four chains: the fp64 adds are dependent otherwise
+#pragma unroll
+      for (int k = 0; k < E; k += 4) {
+        a0 += (double)s_stat[env][k];
+        a1 += (double)s_stat[env][k + 1];
+        a2 += (double)s_stat[env][k + 2];
+        a3 += (double)s_stat[env][k + 3];
+      }
+      double acc = (a0 + a1) + (a2 + a3);
       // reward-term, reward and success entries are means over this shard (trifinger_env.py:554, :1098),
       // the rest are counts (:1067, :1076)
-      const bool is_mean = env < LG_STAT_POSITION_GOAL || env == LG_STAT_SUCCESSES || env == LG_STAT_REWARD;
+      const bool is_mean = env < LG_STAT_POSITION_GOAL || env == LG_STAT_SUCCESSES || env == LG_STAT_REWARD;  // 0..6: terms
       if (is_mean) acc = acc / (double)P.num_envs;
       atomicAdd(B.step_stats + env, acc);
     }
   }
-  emit_outputs();
+  if (full) emit_outputs(std::true_type{});
+  else emit_outputs(std::false_type{});
 }
 
 // history seeding (trifinger_env.py:619-628): both entries = initial simulator state
@@ -685,6 +733,18 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
                (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
   }
+  // extension (no reference code): additive Gaussian action noise, before the clamp
+  if (P.dr_activate && P.dr_action_sigma != 0.0f) {
+#pragma unroll
+    for (int it = 0; it < r_act.ITERS; ++it) {
+      const uint64_t genv = (uint64_t)(P.env_offset + e0 + r_act.grp + it * r_act.G);
+      const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, 0x41435400u + r_act.col, epoch},
+                                 (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+      float n0, n1;
+      box_muller(r.x, r.y, n0, n1);
+      r_act.v[it] = r_act.v[it] + P.dr_action_sigma * n0;
+    }
+  }
   // action store (envs/env_base.py:369) with the wrapper's clamp (wrappers/vec_task.py:162)
   if (P.clip_input_actions) {
     const float clip = P.clip_actions;
@@ -834,14 +894,6 @@ __global__ void lgsk_kernel(const float* x, float scale, float* out, int64_t n) 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = lgsk(x[i], scale);
 }
-// extension: the 8 cube corners (+-s/2)^3 rotated by the pose quaternion and translated
-__device__ __forceinline__ void quat_rotate(const Quat q, float vx, float vy, float vz, float& ox, float& oy, float& oz) {
-  // v' = v + 2 w (q_v x v) + 2 q_v x (q_v x v)
-  const float tx = 2.0f * (q.y * vz - q.z * vy), ty = 2.0f * (q.z * vx - q.x * vz), tz = 2.0f * (q.x * vy - q.y * vx);
-  ox = vx + q.w * tx + (q.y * tz - q.z * ty);
-  oy = vy + q.w * ty + (q.z * tx - q.x * tz);
-  oz = vz + q.w * tz + (q.x * ty - q.y * tx);
-}
 __global__ void keypoints_kernel(const float* pose, float size, float* out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 8) return;
@@ -971,14 +1023,18 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
   if (clip && asym && !B->states_clipped) return fail(LG_ERR_BAD_ARG, "obs_clipped and states_clipped go together");
   LgCoef cf;
   std::memset(&cf, 0, sizeof(cf));
-  if (REWARD) {
-    if (P->use_device_clock) { if (!B->reward_coef) return fail(LG_ERR_BAD_ARG, "use_device_clock needs reward_coef"); }
-    else lg::compute_coefs(*P, sched, cf.v);
+  if (REWARD && P->use_device_clock) {
+    if (!B->reward_coef) return fail(LG_ERR_BAD_ARG, "use_device_clock needs reward_coef");
+  } else {
+    lg::compute_coefs(*P, sched, cf.v);
   }
   const int E = P->action_dim == 9 ? pick_tile_envs(P->num_envs) : 32;
   const unsigned grid = (unsigned)((P->num_envs + E - 1) / E);
   cudaError_t err;
-#define LG_K(AD, AS, CL, EE) launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE>, grid, lg::kPostThreads, st, *P, *S, *B, cf)
+  // extensions (DR noise, keypoint term) live in their own instantiation: switched off they cost nothing
+  const bool ext = P->dr_activate || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1);
+#define LG_K(AD, AS, CL, EE) (ext ? launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, true>, grid, lg::kPostThreads, st, *P, *S, *B, cf) \
+                                  : launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, false>, grid, lg::kPostThreads, st, *P, *S, *B, cf))
 #define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))
   if (P->action_dim == 9) {
     if (asym) err = clip ? LG_E(9, true, true) : LG_E(9, true, false);

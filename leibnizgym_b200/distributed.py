@@ -49,7 +49,7 @@ def stats_to_info(stats: torch.Tensor, active_terms) -> Dict[str, float]:
     """The reference's `_step_info` keys from a statistics vector."""
     v = stats.detach().cpu().tolist()
     out = {}
-    for i, name in enumerate(nat.TERM_NAMES[:6]):
+    for i, name in enumerate(nat.TERM_NAMES):
         if name in active_terms:
             out[f"env/rewards/{name}"] = v[i]
     out["env/current_position_goal/count"] = v[nat.STAT_POSITION_GOAL]

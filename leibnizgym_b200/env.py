@@ -304,8 +304,9 @@ class TrifingerEnv(IsaacEnvBase):
         self._P = build_params(self.config, N, env_offset=self._env_offset, global_num_envs=self._global_N,
                                fingertip_bodies=s.fingertip_bodies, bodies_per_env=s.bodies_per_env,
                                actors_per_env=s.actors_per_env, slots=s.slots)
-        tab = np.zeros((3, nat.LG_MAX_STATE_DIM), np.float32)
+        tab = np.zeros((4, nat.LG_MAX_STATE_DIM), np.float32)
         tab[0], tab[1], tab[2] = self._P.scale_centre, self._P.scale_span, self._P.scale_rcp
+        tab[3] = self._P.dr_sigma
         tab[1][tab[1] == 0] = 1.0
         self._scale_table = torch.as_tensor(tab, device=dev).contiguous()
 
@@ -476,8 +477,8 @@ class TrifingerEnv(IsaacEnvBase):
         of the per-step statistics buffer: valid until the next step overwrites them; values are
         this shard's (see global_step_info)."""
         buf, info = self._step_stats, {}
-        for i, name in enumerate(nat.TERM_NAMES[:6]):
-            if self.config["reward_terms"][name]["activate"]:
+        for i, name in enumerate(nat.TERM_NAMES):
+            if self.config["reward_terms"].get(name, {}).get("activate"):
                 info[f"env/rewards/{name}"] = buf[i]
         info["env/current_position_goal/count"] = buf[nat.STAT_POSITION_GOAL]
         info["env/current_orientation_goal/count"] = buf[nat.STAT_ORIENTATION_GOAL]

@@ -187,7 +187,14 @@ def build_params(cfg: dict, num_local_envs: int, env_offset: int = 0, global_num
     p.clip_obs, p.clip_actions, p.clip_input_actions = 5.0, 1.0, 0
     dr = cfg.get("domain_randomization", {})
     p.dr_activate = int(bool(dr.get("activate", False)))
-    p.dr_action_sigma = float(dr.get("action_noise_std", 0.0))
+    p.dr_action_sigma = float(dr.get("action_noise_std", 0.0)) if p.dr_activate else 0.0
+    if p.dr_activate:  # sigma per RAW observation column, by the obs_spec groups (trifinger_env.py:280-286)
+        std = dr.get("obs_noise_std", {})
+        groups = (("robot_q", 0, 9), ("robot_u", 9, 18), ("object_q", 18, 25), ("object_q_des", 25, 32),
+                  ("command", 32, 32 + A))
+        for name, a, b in groups:
+            for c in range(a, b):
+                p.dr_sigma[c] = float(std.get(name, 0.0))
     p.seed = int(cfg["seed"]) & 0xFFFFFFFFFFFFFFFF
     p.inject_draws = 0
     p.use_device_clock = 0

@@ -1,0 +1,35 @@
+"""CPU restatements of the two EXTENSION features — TEST INFRASTRUCTURE, PARITY UNPINNED.
+
+Neither exists in the reference (`grep -i keypoint|quat_rotate` finds nothing and
+`leibnizgym/dr/__init__.py` is empty), so there is no reference output to pin against; these
+functions state the definitions the CUDA kernels implement in plain torch.
+"""
+from __future__ import annotations
+
+import torch
+
+CUBE_SIZE = 0.065
+
+
+def quat_rotate(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Rotate v [...,3] by unit quaternion q [...,4] (xyzw): v + 2 w (q_v x v) + 2 q_v x (q_v x v)."""
+    qv, w = q[..., :3], q[..., 3:4]
+    t = 2.0 * torch.cross(qv, v, dim=-1)
+    return v + w * t + torch.cross(qv, t, dim=-1)
+
+
+def cube_keypoints(pose: torch.Tensor, size: float = CUBE_SIZE) -> torch.Tensor:
+    """[n,7] poses -> [n,8,3] world-frame corners; corner k has signs (bit0, bit1, bit2) of k."""
+    h = size / 2
+    corners = torch.tensor([[(h if k & 1 else -h), (h if k & 2 else -h), (h if k & 4 else -h)] for k in range(8)],
+                           dtype=pose.dtype)
+    p, q = pose[:, None, 0:3], pose[:, None, 3:7].expand(-1, 8, -1)
+    return p + quat_rotate(q, corners[None].expand(pose.shape[0], -1, -1))
+
+
+def keypoint_reward(weight: float, dt: float, obj_pose: torch.Tensor, goal_pose: torch.Tensor,
+                    scale: float = 30.0, eps: float = 2.0) -> torch.Tensor:
+    """w dt mean_k 1 / (e^{s d_k} + eps + e^{-s d_k}),  d_k = |kp_k(object) - kp_k(goal)|."""
+    d = torch.norm(cube_keypoints(obj_pose) - cube_keypoints(goal_pose), p=2, dim=-1)
+    s = d * scale
+    return (weight * dt) * (1.0 / (s.exp() + eps + (-s).exp())).mean(dim=-1)

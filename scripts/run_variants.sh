@@ -1,5 +1,8 @@
-for m in "--e2e-mode copy" "--e2e-mode copy --e2e-full-upload"; do python bench.py --steps 2048 --warmup 128 --no-cpu --e2e-steps 200 $m > gpurun_out/bench_e2e.json 2>gpurun_out/err_e2e.log; python -c "
+python -m pytest tests -m gpu -q --tb=line 2>&1 | tail -4
+run() { tag=$1; shift; env "$@" python bench.py --steps 8192 --warmup 256 --no-cpu --e2e-steps 100 $EXTRA > gpurun_out/bench_$tag.json 2>gpurun_out/err_$tag.log; python -c "
 import json
-d=json.load(open('gpurun_out/bench_e2e.json'))
-print('$m', d['e2e'])"; tail -2 gpurun_out/err_e2e.log; done
-python -m pytest tests -m gpu -q 2>&1 | tail -3
+d=json.load(open('gpurun_out/bench_$tag.json'))
+print('$tag', 'step_us', round(d['ms_per_step']*1e3,2), 'post_us', round(d['roofline']['launch_us'],2), 'frac', round(d['roofline']['frac'],3), 'value', round(d['value']/1e9,3), 'e2e', round(d['e2e']['value']/1e6,2))"; tail -2 gpurun_out/err_$tag.log; }
+EXTRA="" run v13 LG_X=1
+EXTRA="" run v13_e32 LG_TILE_ENVS=32
+EXTRA="--envs 262144 --ring 8 --steps 1024" run v13_big LG_X=1

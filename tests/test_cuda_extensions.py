@@ -1,0 +1,106 @@
+"""The two extension features the north star names but the reference does not implement:
+the keypoint pose reward (against oracle/extensions.py) and the DR observation / action noise (stated
+distributional check).  Both default off; switched off they leave the path bit-identical."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(cfg, seq, N):
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    env.enable_term_rewards(True)
+    return env
+
+
+def test_keypoint_reward_term():
+    from leibnizgym_b200.config import difficulty_config, resolve_config
+    from leibnizgym_b200.synthetic import make_sequence
+    from oracle.extensions import keypoint_reward
+    from oracle.trifinger_oracle import OracleEnv, OracleSim
+    N, T = 4096, 3
+    base = difficulty_config(4, N, seed=3)
+    cfg = copy.deepcopy(base)
+    cfg["reward_terms"]["keypoint"] = {"activate": True, "weight": 1500, "scale": 30.0, "eps": 2.0}
+    seq = make_sequence(41, T, N)
+    # bring a third of the cubes close to their goals so the kernel term is not all ~0
+    env = _make(cfg, seq, N)
+    ora = OracleEnv(resolve_config(base), OracleSim(seq, N))
+    g = torch.Generator().manual_seed(1)
+    d = (torch.rand(N, 24, generator=g).numpy(), torch.randn(N, 8, generator=g).numpy())
+    env.inject_draws(reset=d)
+    ora.inject_draws(reset=d)
+    env.reset()
+    ora.reset()
+    goal = ora.goal_poses.clone()
+    near = torch.arange(0, N, 3)
+    root = seq.root_state.view(T, N, 4, 13)
+    root[1:, near, 2, 0:3] = goal[near, 0:3] + 0.01 * torch.randn(len(near), 3, generator=g)
+    root[1:, near, 2, 3:7] = torch.nn.functional.normalize(goal[near, 3:7] + 0.05 * torch.randn(len(near), 4, generator=g), dim=-1)
+    env._sim.seq = seq.to("cuda:0")
+    for t in range(1, T):
+        env.step(seq.action[t].cuda())
+        ora.step(seq.action[t].clone())
+        exp_kp = keypoint_reward(1500, 0.02, ora.obj_hist[0][:, 0:7], ora.goal_poses)
+        got_kp = env._term_rewards[6].cpu()
+        assert float(exp_kp.max()) > 1.0                                  # the term is exercised
+        np.testing.assert_allclose(got_kp.numpy(), exp_kp.numpy(), rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(env.reward_buf.cpu().numpy(), (ora.reward_buf + exp_kp).numpy(), rtol=2e-5, atol=5e-4)
+        info = env._step_info
+        assert abs(float(info["env/rewards/keypoint"]) - float(exp_kp.double().mean())) < 1e-4
+        assert abs(float(info["env/rewards/object_dist"]) - float(ora.step_info["env/rewards/object_dist"])) < 1e-4
+
+
+def test_dr_noise_off_is_bit_identical_and_on_is_gaussian():
+    from scipy import stats
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.params import observation_scale
+    from leibnizgym_b200.config import resolve_config
+    from leibnizgym_b200.synthetic import make_sequence
+    N, T = 120_000, 3
+    seq = make_sequence(51, T, N)
+    seq.action.mul_(0.5)                                              # keep the noisy action inside the clamp
+    base = difficulty_config(3, N, seed=9)
+    sig = {"robot_q": 0.01, "robot_u": 0.05, "object_q": 0.002, "object_q_des": 0.0, "command": 0.0}
+    dr_off = dict(copy.deepcopy(base), domain_randomization={"activate": True, "action_noise_std": 0.0,
+                                                             "obs_noise_std": {k: 0.0 for k in sig}})
+    dr_on = dict(copy.deepcopy(base), domain_randomization={"activate": True, "action_noise_std": 0.03, "obs_noise_std": sig})
+
+    def run(cfg, steps=2):
+        env = _make(cfg, seq, N)
+        env.enable_clipped_outputs(5.0, 1.0)
+        env.reset()
+        outs = []
+        for t in range(1, 1 + steps):
+            env.step(seq.action[t].cuda())
+            outs.append((env.obs_buf.clone(), env.states_buf.clone(), env.action_buf.clone(), env.reward_buf.clone()))
+        return outs
+
+    clean, off, on, on2 = run(base), run(dr_off), run(dr_on), run(dr_on)
+    for a, b in zip(clean, off):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))          # sigma = 0 -> the reference path, bit for bit
+    for a, b in zip(on, on2):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))          # deterministic in (seed, step, env)
+    lo, hi = observation_scale(resolve_config(base))
+    half = torch.tensor((hi - lo) / 2).cuda()
+    resid = [((on[t][0] - clean[t][0]) * half).cpu().numpy().astype(np.float64) for t in range(2)]
+    assert torch.equal(on[0][1][:, 41:], clean[0][1][:, 41:])        # privileged part of the critic state stays clean
+    assert torch.equal(on[0][1][:, :32], clean[0][1][:, :32])        # ... and so does its copy of the observation
+    assert not torch.equal(on[0][1][:, 32:41], clean[0][1][:, 32:41])  # (the stored action itself is the noisy one)
+    for col, s in ((0, 0.01), (5, 0.01), (9, 0.05), (17, 0.05), (18, 0.002), (24, 0.002)):
+        r = resid[0][:, col]
+        assert abs(r.mean()) < 4 * s / np.sqrt(N) and abs(r.std() / s - 1) < 0.02, (col, r.mean(), r.std())
+        assert stats.kstest(r / s, "norm").pvalue > 1e-3, col
+    assert np.abs(resid[0][:, 25:32]).max() == 0.0                   # sigma 0 group (goal pose) untouched
+    # independence: across steps, across envs, across columns
+    assert abs(np.corrcoef(resid[0][:, 9], resid[1][:, 9])[0, 1]) < 0.01
+    assert abs(np.corrcoef(resid[0][:-1, 9], resid[0][1:, 9])[0, 1]) < 0.01
+    assert abs(np.corrcoef(resid[0][:, 9], resid[0][:, 10])[0, 1]) < 0.01
+    # action noise: additive N(0, 0.03^2) before the clamp (|action| <= 0.5 here, so the clamp is inactive)
+    ra = (on[0][2] - clean[0][2]).cpu().numpy().astype(np.float64)
+    assert abs(ra.std() / 0.03 - 1) < 0.02 and stats.kstest(ra[:, 3] / 0.03, "norm").pvalue > 1e-3
