@@ -369,7 +369,9 @@ def run_e2e(args, wl, cfg, dev, rank, world):
     env = TrifingerEnv(cfg, device=dev, verbose=False, sim=sim, rank=rank, world_size=world)
     if mode != "zc" and not args.e2e_full_upload:
         sim.use_sparse_upload(env._P)
-    vec = VecTaskPython(env, rl_device=dev if mode == "copy" else "cpu", clip_obs=5.0, clip_actions=1.0)
+    chunks = args.e2e_chunks if mode == "copy" else 0
+    vec = VecTaskPython(env, rl_device=dev if (mode == "copy" and not chunks) else "cpu", clip_obs=5.0, clip_actions=1.0,
+                        host_pipeline_chunks=chunks)
     vec.reset()
     obs_dim, st_dim = env.get_obs_dim(), env.get_state_dim()
     if mode == "copy":
@@ -382,14 +384,14 @@ def run_e2e(args, wl, cfg, dev, rank, world):
     def one(t):
         obs, rew, done, _ = vec.step(host.action[t % T])   # pinned host action
         states = vec.get_state() if asym else None
-        if mode == "copy":
+        if mode == "copy" and not chunks:
             h_obs.copy_(obs, non_blocking=True)
             h_rew.copy_(rew, non_blocking=True)
             h_done.copy_(done, non_blocking=True)
             if asym:
                 h_states.copy_(states, non_blocking=True)
         torch.cuda.synchronize()                           # the caller consumes the results every step
-        return obs if mode != "copy" else h_obs
+        return obs if (mode != "copy" or chunks) else h_obs
 
     for t in range(3):
         one(t)
@@ -415,7 +417,7 @@ def run_e2e(args, wl, cfg, dev, rank, world):
     d2h = 4 * N * (obs_dim + st_dim + 1 + (0 if mode == "copy" else 9)) + N   # zero-copy modes also return the torque
     return {"value": steps * N * world / (ms * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": zc_h2d if mode == "zc" else full_h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": ms / steps, "mode": mode,
+            "steps": steps, "ms_per_step": ms / steps, "mode": mode, "pipeline_chunks": chunks,
             "api": "VecTaskPython.step + get_state; simulator state, action and results in pinned host memory"}
 
 
@@ -430,6 +432,7 @@ def main():
     ap.add_argument("--ring", type=int, default=32, help="distinct simulator states in HBM")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-mode", default="copy", choices=["zc", "zc_out", "copy"])
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="env ranges of the host pipeline (0 = un-chunked copies)")
     ap.add_argument("--e2e-full-upload", action="store_true", help="upload all 20 rigid bodies, not just the fingertip run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")

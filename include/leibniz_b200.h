@@ -117,6 +117,8 @@ typedef struct LgParams {
                                (env_base.py:391-399); 0 = _post_step semantics only              */
   int32_t term_active_mask; /* bit k = terms[k].activate                                        */
   uint64_t seed;
+  int64_t stats_num_envs;   /* denominator of the statistics means; 0 = num_envs.  Lets a caller run the
+                               post-physics pass over sub-ranges of a shard (chunked host pipeline)      */
   /* ---- cold block ---- */
   double dt;                /* config["sim"]["dt"]                                               */
   double success_bonus, position_tolerance, orientation_tolerance;
@@ -304,6 +306,16 @@ typedef struct LgHostStep {
 int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep* H, void* stream);
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B,
                  const LgHostStep* H, double sched_step, void* stream);
+
+/*
+ * lg_step_host with the shard cut into `chunks` env ranges and pipelined over three streams: uploads on
+ * `stream_up`, kernels on `stream_main`, downloads on `stream_down` (PCIe is full duplex, so the upload of range
+ * c+1 overlaps the kernels of range c and the download of range c-1).  lg_pre_physics runs once over the whole
+ * shard (its ordered compaction spans it); lg_post_physics runs per range on offset pointers.  All outputs are
+ * valid once `stream_main` is synchronised.  Results are identical to lg_step_host.
+ */
+int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H,
+                           double sched_step, int chunks, void* stream_main, void* stream_up, void* stream_down);
 
 #ifdef __cplusplus
 }

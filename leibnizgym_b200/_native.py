@@ -50,6 +50,7 @@ class LgParams(C.Structure):
         ("clip_obs", C.c_float), ("clip_actions", C.c_float), ("clip_input_actions", C.c_int32),
         ("dr_activate", C.c_int32), ("inject_draws", C.c_int32), ("use_device_clock", C.c_int32),
         ("fuse_bookkeeping", C.c_int32), ("term_active_mask", C.c_int32), ("seed", C.c_uint64),
+        ("stats_num_envs", C.c_int64),
         ("dt", C.c_double), ("success_bonus", C.c_double), ("position_tolerance", C.c_double),
         ("orientation_tolerance", C.c_double), ("dof_pos_stddev", C.c_double), ("dof_vel_stddev", C.c_double),
         ("goal_rate_magnitude", C.c_double),
@@ -117,6 +118,7 @@ SYMBOLS = {
     "lg_cube_keypoints": (C.c_int, [_vp, C.c_float, _vp, _i64, _vp]),
     "lg_selftest_division": (C.c_int, [C.c_float, C.c_float, _vp, _vp]),
     "lg_upload_sim_state": (C.c_int, [_P, _S, C.POINTER(LgHostStep), _vp]),
+    "lg_step_host_pipelined": (C.c_int, [_P, _S, _B, C.POINTER(LgHostStep), C.c_double, C.c_int, _vp, _vp, _vp]),
     "lg_step_host": (C.c_int, [_P, _S, _B, C.POINTER(LgHostStep), C.c_double, _vp]),
 }
 

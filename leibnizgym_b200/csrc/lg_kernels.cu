@@ -540,7 +540,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       // reward-term, reward and success entries are means over this shard (trifinger_env.py:554, :1098),
       // the rest are counts (:1067, :1076)
       const bool is_mean = env < LG_STAT_POSITION_GOAL || env == LG_STAT_SUCCESSES || env == LG_STAT_REWARD;  // 0..6: terms
-      if (is_mean) acc = acc / (double)P.num_envs;
+      if (is_mean) acc = acc / (double)(P.stats_num_envs > 0 ? P.stats_num_envs : P.num_envs);
       atomicAdd(B.step_stats + env, acc);
     }
   }
@@ -1202,6 +1202,76 @@ int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep
     cudaMemcpyAsync(const_cast<float*>(S->ft_sensors), H->ft_sensors_host, sizeof(float) * N * 18, k, st);
   }
   return check_launch("lg_upload_sim_state");
+}
+
+int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H,
+                           double sched_step, int chunks, void* stream_main, void* stream_up, void* stream_down) {
+  if (int rc = validate(P, S, B, true)) return rc;
+  if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||
+      !H->obs_host || !H->reward_host)
+    return fail(LG_ERR_BAD_ARG, "null host buffer");
+  if (chunks < 1 || chunks > 16) return fail(LG_ERR_BAD_ARG, "chunks must be in 1..16");
+  if (P->asymmetric_obs && (!H->dof_force_host || !H->ft_sensors_host || !H->states_host))
+    return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
+  cudaStream_t main = (cudaStream_t)stream_main, up = (cudaStream_t)stream_up, down = (cudaStream_t)stream_down;
+  // events are created once per host thread and reused (timing disabled: cheapest kind)
+  struct Pool { cudaEvent_t pre, done, up[16], post[16]; bool ok = false; };
+  static thread_local Pool pool;
+  if (!pool.ok) {
+    const unsigned f = cudaEventDisableTiming;
+    cudaEventCreateWithFlags(&pool.pre, f); cudaEventCreateWithFlags(&pool.done, f);
+    for (int i = 0; i < 16; ++i) { cudaEventCreateWithFlags(&pool.up[i], f); cudaEventCreateWithFlags(&pool.post[i], f); }
+    pool.ok = true;
+  }
+  const int64_t N = P->num_envs;
+  const int A = P->action_dim, od = 32 + A, sd = P->asymmetric_obs ? od + 72 : 0;
+  const float* obs_src = B->obs_clipped ? B->obs_clipped : B->obs;
+  const float* st_src = B->states_clipped ? B->states_clipped : B->states;
+  // the action arrives first; resets / torque consume it together with the previous state
+  cudaMemcpyAsync(H->action_staging, H->action_host, sizeof(float) * N * A, cudaMemcpyHostToDevice, main);
+  if (int rc = lg_pre_physics(P, S, B, H->action_staging, stream_main)) return rc;
+  cudaEventRecord(pool.pre, main);
+  cudaStreamWaitEvent(up, pool.pre, 0);
+  int64_t lo = 0;
+  for (int c = 0; c < chunks; ++c) {
+    int64_t hi = c == chunks - 1 ? N : ((N * (c + 1) / chunks + 16) / 32) * 32;
+    if (hi > N) hi = N;
+    if (hi <= lo) continue;
+    LgParams pc = *P;
+    pc.num_envs = hi - lo; pc.env_offset = P->env_offset + lo; pc.stats_num_envs = N; pc.fuse_bookkeeping = 1;
+    LgSimState sc = *S;
+    sc.dof_state += lo * 18; sc.root_state += lo * 13 * P->actors_per_env; sc.rigid_body += lo * 13 * P->bodies_per_env;
+    if (sc.dof_force) sc.dof_force += lo * 9;
+    if (sc.ft_sensors) sc.ft_sensors += lo * 18;
+    LgHostStep hc = *H;
+    hc.dof_state_host += lo * 18; hc.root_state_host += lo * 13 * P->actors_per_env;
+    hc.rigid_body_host += lo * 13 * P->bodies_per_env;
+    if (hc.dof_force_host) hc.dof_force_host += lo * 9;
+    if (hc.ft_sensors_host) hc.ft_sensors_host += lo * 18;
+    LgBuffers bc = *B;
+    bc.obs += lo * od; if (bc.states) bc.states += lo * sd;
+    if (bc.obs_clipped) bc.obs_clipped += lo * od;
+    if (bc.states_clipped) bc.states_clipped += lo * sd;
+    bc.action += lo * A; bc.reward += lo; bc.reset += lo; bc.goal_reset += lo; bc.successes += lo;
+    if (bc.dones) bc.dones += lo;
+    bc.steps_count += lo; bc.goal_pose += lo * 7; bc.goal_movement += lo * 6; bc.history += lo * LG_HISTORY_COLS;
+    if (bc.applied_torque) bc.applied_torque += lo * 9;
+    bc.term_rewards = nullptr;
+    if (int rc = lg_upload_sim_state(&pc, &sc, &hc, stream_up)) return rc;
+    cudaEventRecord(pool.up[c], up);
+    cudaStreamWaitEvent(main, pool.up[c], 0);
+    if (int rc = lg_post_physics(&pc, &sc, &bc, sched_step, stream_main)) return rc;
+    cudaEventRecord(pool.post[c], main);
+    cudaStreamWaitEvent(down, pool.post[c], 0);
+    cudaMemcpyAsync(H->obs_host + lo * od, obs_src + lo * od, sizeof(float) * (hi - lo) * od, cudaMemcpyDeviceToHost, down);
+    if (sd) cudaMemcpyAsync(H->states_host + lo * sd, st_src + lo * sd, sizeof(float) * (hi - lo) * sd, cudaMemcpyDeviceToHost, down);
+    cudaMemcpyAsync(H->reward_host + lo, B->reward + lo, sizeof(float) * (hi - lo), cudaMemcpyDeviceToHost, down);
+    if (H->dones_host && B->dones) cudaMemcpyAsync(H->dones_host + lo, B->dones + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, down);
+    lo = hi;
+  }
+  cudaEventRecord(pool.done, down);
+  cudaStreamWaitEvent(main, pool.done, 0);
+  return check_launch("lg_step_host_pipelined");
 }
 
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {

@@ -82,6 +82,16 @@ class SyntheticSim:
         self.cursor += 1
         self.frame_count += 1
 
+    def begin_step(self) -> int:
+        """Advance the simulator clock WITHOUT staging the new state; returns the sequence index of that
+        state.  For callers that upload it themselves in pieces (host_pipeline.HostPipeline)."""
+        if self.before_simulate is not None:
+            self.before_simulate(self)
+        t = self.cursor % self.seq.num_steps
+        self.cursor += 1
+        self.frame_count += 1
+        return t
+
     def get_frame_count(self) -> int:
         return self.frame_count
 

@@ -94,17 +94,27 @@ class VecTask:
 
 
 class VecTaskPython(VecTask):
-    def __init__(self, task: IsaacEnvBase, rl_device: str, clip_obs: float = 5.0, clip_actions: float = 1.0):
+    def __init__(self, task: IsaacEnvBase, rl_device: str, clip_obs: float = 5.0, clip_actions: float = 1.0,
+                 host_pipeline_chunks: int = 0):
+        """`host_pipeline_chunks` > 0 (host-resident simulator and learner, rl_device 'cpu'): step through
+        host_pipeline.HostPipeline, which overlaps the state upload, the kernels and the result download."""
         super().__init__(task, rl_device, clip_obs, clip_actions)
+        self._pipeline = None
         self._fused = hasattr(task, "enable_clipped_outputs")
         if self._fused:
-            if torch.device(rl_device).type == "cpu" and hasattr(task, "enable_host_outputs"):
+            if host_pipeline_chunks > 0:
+                from ..host_pipeline import HostPipeline
+                task.enable_clipped_outputs(self._clip_obs, self._clip_actions)
+                self._pipeline = HostPipeline(task, chunks=host_pipeline_chunks)
+            elif torch.device(rl_device).type == "cpu" and hasattr(task, "enable_host_outputs"):
                 # host-side learner: the clipped results are stored straight into pinned host memory
                 task.enable_host_outputs(self._clip_obs, self._clip_actions)
             else:
                 task.enable_clipped_outputs(self._clip_obs, self._clip_actions)
 
     def get_state(self) -> torch.Tensor:
+        if self._pipeline is not None:
+            return self._pipeline.h_states
         if self._fused and self._task._states_clipped is not None:
             return self._task._states_clipped.to(self._rl_device)
         return torch.clamp(self._task.states_buf, -self._clip_obs, self._clip_obs).to(self._rl_device)
@@ -116,6 +126,8 @@ class VecTaskPython(VecTask):
     def step(self, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         if self._task.visualize:
             self._task.render()
+        if self._pipeline is not None:
+            return self._pipeline.step(actions)   # pinned host tensors, valid once the stream is synchronised
         if self._fused:
             # action clamp, obs clamp and states clamp all happen inside the two fused launches
             _, rew, is_done, info = self._task.step(actions)

@@ -44,7 +44,7 @@ def test_struct_layouts_agree():
                                     _native.LgRewardTerm, _native.LgHostStep)):
         assert lib.lg_struct_size(which) == ctypes.sizeof(struct), struct.__name__
     # the hot block of LgParams must stay inside the first two constant-cache lines
-    assert _native.LgParams.seed.offset + 8 <= 160
+    assert _native.LgParams.stats_num_envs.offset + 8 <= 168
 
 
 def test_argument_errors_without_gpu():

@@ -246,3 +246,39 @@ def test_own_random_stream_distributions():
     # a second reset call draws fresh numbers (the epoch advanced)
     env._reset_impl(torch.arange(N, device="cuda:0"))
     assert not np.array_equal(goal, env._object_goal_poses_buf.cpu().numpy().astype(np.float64))
+
+
+def test_host_pipeline_equals_plain_step():
+    """The chunked upload / compute / download pipeline for host-resident simulators returns exactly what
+    the plain step returns (chunks on ragged boundaries, resets and statistics included)."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from leibnizgym_b200.wrappers import VecTaskPython
+    N, T = 10_000, 6
+    cfg = difficulty_config(4, N, seed=17, episode_length=2)
+    host = make_sequence(61, T, N).to("cpu", pin=True)
+
+    def build(chunks):
+        sim = SyntheticSim(host, "cuda:0")
+        env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=sim)
+        sim.use_sparse_upload(env._P)
+        vec = VecTaskPython(env, rl_device="cuda:0" if not chunks else "cpu", host_pipeline_chunks=chunks)
+        vec.reset()
+        return env, vec
+
+    env_a, plain = build(0)
+    env_b, piped = build(3)
+    for t in range(1, T):
+        o1, r1, d1, i1 = plain.step(host.action[t])
+        s1 = plain.get_state()
+        o2, r2, d2, i2 = piped.step(host.action[t])
+        s2 = piped.get_state()
+        torch.cuda.synchronize()
+        assert torch.equal(o1.cpu(), o2) and torch.equal(s1.cpu(), s2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
+        assert torch.equal(env_a._reset_buf, env_b._reset_buf) and torch.equal(env_a._history, env_b._history)
+        assert torch.equal(env_a._object_goal_poses_buf, env_b._object_goal_poses_buf)
+        for k in i1:
+            assert abs(float(i1[k]) - float(i2[k])) <= 1e-9 * max(1.0, abs(float(i1[k]))), k
+    assert int(env_a._steps_count_buf.max()) <= 2 and o2.device.type == "cpu" and o2.is_pinned()
