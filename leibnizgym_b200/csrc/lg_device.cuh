@@ -139,13 +139,30 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 // [0, 1) with 24 random bits, the resolution of torch's CPU float uniform
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 
+// sin and cos of x in [0, 2 pi] (all sampler angles are), ~1 ulp, without the libdevice calls' large-argument
+// slow path: the reset code is executed by a handful of warps per SM, so its latency is its instruction count.
+// Quadrant reduction with a 3-term split of pi/2 whose products with k <= 4 are exact, cephes minimax kernels.
+__device__ __forceinline__ void sincos_2pi(float x, float& s, float& c) {
+  const float kf = rintf(x * 0.636619772367581343f);
+  float r = x - kf * 1.5703125f;
+  r = r - kf * 4.837512969970703125e-4f;
+  r = r - kf * 7.54978995489188216e-8f;
+  const float z = r * r;
+  const float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+  const float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+  const int k = (int)kf & 3;
+  s = (k == 0) ? sp : (k == 1) ? cp : (k == 2) ? -sp : -cp;
+  c = (k == 0) ? cp : (k == 1) ? -sp : (k == 2) ? -cp : sp;
+}
+
 // Box-Muller pair from two 32-bit words
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;  // (0, 1]
   const float r = sqrtf(-2.0f * logf(u1));
-  const float th = kTwoPi * u01(b);
-  n0 = r * cosf(th);
-  n1 = r * sinf(th);
+  float sn, cs;
+  sincos_2pi(kTwoPi * u01(b), sn, cs);
+  n0 = r * cs;
+  n1 = r * sn;
 }
 
 enum DrawPurpose : uint32_t { kPurposeReset = 0x52455345u, kPurposeGoal = 0x474f414cu, kPurposeNoise = 0x4e4f4953u };
@@ -212,14 +229,16 @@ __device__ __forceinline__ DrawSource make_draws(const LgParams& P, uint64_t epo
 __device__ __forceinline__ void sample_disc(float u0, float u1, float radius_max, float& x, float& y) {
   float r = sqrtf(u0);
   r = r * radius_max;
-  const float th = kTwoPi * u1;
-  x = r * cosf(th);
-  y = r * sinf(th);
+  float sn, cs;
+  sincos_2pi(kTwoPi * u1, sn, cs);
+  x = r * cs;
+  y = r * sn;
 }
 // random_yaw_orientation -> quaternion_from_euler_xyz(0, 0, 2 pi u) (sample.py:77-84, torch_utils.py:153-180)
 __device__ __forceinline__ Quat sample_yaw(float u) {
-  const float half = (kTwoPi * u) * 0.5f;
-  return Quat{0.0f, 0.0f, sinf(half), cosf(half)};
+  float sn, cs;
+  sincos_2pi((kTwoPi * u) * 0.5f, sn, cs);
+  return Quat{0.0f, 0.0f, sn, cs};
 }
 // random_orientation: normalize(randn(4), eps=1e-12) (sample.py:55-65); ATen's 2-norm over a
 // contiguous 4-vector accumulates without contraction

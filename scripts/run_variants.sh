@@ -1,8 +1,8 @@
+python -m pytest tests -m gpu -q --tb=line 2>&1 | tail -4
 run() { tag=$1; shift; env "$@" python bench.py --steps 8192 --warmup 256 --no-cpu --e2e-steps 20 $EXTRA > gpurun_out/bench_$tag.json 2>gpurun_out/err_$tag.log; python -c "
 import json
 d=json.load(open('gpurun_out/bench_$tag.json'))
 print('$tag', 'step_us', round(d['ms_per_step']*1e3,2), 'post_us', round(d['roofline']['launch_us'],2), 'frac', round(d['roofline']['frac'],3), 'value', round(d['value']/1e9,3))"; tail -2 gpurun_out/err_$tag.log; }
-EXTRA="" run c5_e24 LG_CTAS_PER_SM=5
-EXTRA="" run c5_e28 LG_TILE_ENVS=28
-EXTRA="" run c5_e32 LG_TILE_ENVS=32
-EXTRA="--envs 262144 --ring 8 --steps 1024" run c5_big LG_X=1
+EXTRA="" run v15 LG_X=1
+EXTRA="" run v15b LG_X=1
+EXTRA="--envs 262144 --ring 8 --steps 1024" run v15_big LG_X=1
