@@ -661,15 +661,51 @@ __device__ __noinline__ void reset_cold(const LgParams& P, const LgSimState& S, 
   }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): one thread moves a whole contiguous tile slab -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int A, bool TICKET>
 __global__ void __launch_bounds__(kPreThreads)
 pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                    const __grid_constant__ LgBuffers B,
                    const float* __restrict__ action_in, int num_tiles) {
   constexpr int E = kPreThreads, NT = kPreThreads;
-  __shared__ float s_act[E * A];
-  __shared__ float s_dof[E * 18];
-  __shared__ float s_tq[E * 9];
+  // tile slabs: the action and joint-state rows of the tile's 128 envs are contiguous in memory, so they
+  // come in (and the action / torque rows go out) as TMA bulk copies issued by one thread
+  __shared__ __align__(128) float s_act[E * A];
+  __shared__ __align__(128) float s_dof[E * 18];
+  __shared__ __align__(128) float s_tq[E * 9];
+  __shared__ __align__(8) uint64_t s_mbar;
   __shared__ int s_tile;
   __shared__ uint32_t s_wa[NT / 32], s_wb[NT / 32];
   const int tid = threadIdx.x;
@@ -687,14 +723,26 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
   const bool live = tid < nvalid;
   const bool want_torque = B.applied_torque != nullptr;
+  const bool full_tile = nvalid == E;   // bulk copies need 16-byte multiples: ragged last tile goes lane by lane
 
   // ---- every global load of the tile up front ---------------------------------------------------
+  if (full_tile) {
+    if (tid == 0) {
+      mbar_init(&s_mbar, 1);
+      mbar_expect_tx(&s_mbar, (uint32_t)(sizeof(float) * E * (A + (want_torque ? 18 : 0))));
+      bulk_load(s_act, action_in + e0 * A, sizeof(float) * E * A, &s_mbar);
+      if (want_torque) bulk_load(s_dof, S.dof_state + e0 * 18, sizeof(float) * E * 18, &s_mbar);
+    }
+  } else if (live) {
+#pragma unroll
+    for (int c = 0; c < A; ++c) s_act[tid * A + c] = action_in[e * A + c];
+    if (want_torque) {
+#pragma unroll
+      for (int c = 0; c < 18; ++c) s_dof[tid * 18 + c] = S.dof_state[e * 18 + c];
+    }
+  }
   uint8_t flag_r = 0, flag_g = 0;
   if (live) { flag_r = B.reset[e]; flag_g = B.goal_reset[e]; }
-  ColSlab<A, E, NT> r_act;
-  ColSlab<18, E, NT> r_dof;
-  r_act.load(action_in + (e0 + r_act.grp) * A + r_act.col, A, nvalid);
-  if (want_torque) r_dof.load(S.dof_state + (e0 + r_dof.grp) * 18 + r_dof.col, 18, nvalid);
   pdl_launch_dependents();
   if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
   if (tile == 0 && tid == NT - 1 && P.use_device_clock) {
@@ -708,12 +756,12 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
 
   // ---- block scan of both masks + aggregate publication (env_base.py:374-379) -------------------
   // Needs only the two flag bytes, so it runs (and the tile's aggregate is visible to its successors)
-  // while the action / joint-state loads are still in flight; the look-back at the end then never waits.
+  // while the action / joint-state slabs are still in flight; the look-back at the end then never waits.
   const bool f_reset = flag_r != 0, f_goal = flag_g != 0;
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned ba = __ballot_sync(0xffffffffu, f_reset), bb = __ballot_sync(0xffffffffu, f_goal);
   if (lane == 0) { s_wa[warp] = __popc(ba); s_wb[warp] = __popc(bb); }
-  __syncthreads();
+  __syncthreads();   // also orders the mbarrier initialisation before the waits below
   TileScan t;
   t.tile = tile; t.epoch = epoch;
   {
@@ -733,50 +781,64 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
                (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
   }
-  // extension (no reference code): additive Gaussian action noise, before the clamp
-  if (P.dr_activate && P.dr_action_sigma != 0.0f) {
-#pragma unroll
-    for (int it = 0; it < r_act.ITERS; ++it) {
-      const uint64_t genv = (uint64_t)(P.env_offset + e0 + r_act.grp + it * r_act.G);
-      const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, 0x41435400u + r_act.col, epoch},
-                                 (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-      float n0, n1;
-      box_muller(r.x, r.y, n0, n1);
-      r_act.v[it] = r_act.v[it] + P.dr_action_sigma * n0;
-    }
-  }
-  // action store (envs/env_base.py:369) with the wrapper's clamp (wrappers/vec_task.py:162)
-  if (P.clip_input_actions) {
-    const float clip = P.clip_actions;
-#pragma unroll
-    for (int it = 0; it < r_act.ITERS; ++it) r_act.v[it] = fminf(fmaxf(r_act.v[it], -clip), clip);
-  }
-  r_act.drain(s_act + r_act.grp * A + r_act.col, A, nvalid);
-  if (want_torque) r_dof.drain(s_dof + r_dof.grp * 18 + r_dof.col, 18, nvalid);
-  __syncthreads();
   uint32_t ex_a = 0, ex_b = 0;
   const bool need_rank_first = P.inject_draws != 0;  // injected draws are indexed by compaction rank
   if (need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
 
-  // ---- resets (cold) -------------------------------------------------------------------------------
-  if (f_reset || f_goal) {
-    if (f_reset) {
-#pragma unroll
-      for (int c = 0; c < A; ++c) s_act[tid * A + c] = 0.0f;  // the row is zeroed after the store (:387)
-    }
-    reset_cold(P, S, B, e, f_reset, f_goal, (int64_t)ex_a + t.rank_a, (int64_t)ex_b + t.rank_b, (uint64_t)epoch);
-  }
-  // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
-  if (want_torque && live) {
-    float act[A];
+  if (full_tile) mbar_wait(&s_mbar, 0);   // the slabs have landed (each thread only touches its own env row below)
+
+  // ---- this env's action row: noise (extension), clamp, reset ---------------------------------------
+  float act[A];
+  if (live) {
 #pragma unroll
     for (int c = 0; c < A; ++c) act[c] = s_act[tid * A + c];
+    if (P.dr_activate && P.dr_action_sigma != 0.0f) {  // extension (no reference code): Gaussian action noise
+      const uint64_t genv = (uint64_t)(P.env_offset + e);
+#pragma unroll
+      for (int c = 0; c < A; ++c) {
+        const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, 0x41435400u + c, epoch},
+                                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        float n0, n1;
+        box_muller(r.x, r.y, n0, n1);
+        act[c] = act[c] + P.dr_action_sigma * n0;
+      }
+    }
+    if (P.clip_input_actions) {   // the wrapper's clamp (wrappers/vec_task.py:162)
+      const float clip = P.clip_actions;
+#pragma unroll
+      for (int c = 0; c < A; ++c) act[c] = fminf(fmaxf(act[c], -clip), clip);
+    }
+    if (f_reset) {                // the row is zeroed after the store (envs/env_base.py:369, trifinger_env.py:387)
+#pragma unroll
+      for (int c = 0; c < A; ++c) act[c] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < A; ++c) s_act[tid * A + c] = act[c];
+  }
+  // ---- resets (cold) -------------------------------------------------------------------------------
+  if (f_reset || f_goal)
+    reset_cold(P, S, B, e, f_reset, f_goal, (int64_t)ex_a + t.rank_a, (int64_t)ex_b + t.rank_b, (uint64_t)epoch);
+  // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
+  if (want_torque && live) {
     const bool dof_rewritten = f_reset && P.robot_reset != LG_RESET_NONE;
     torque_one_env(P, act, dof_rewritten ? S.dof_state + e * 18 : s_dof + tid * 18, s_tq + tid * 9);
   }
-  __syncthreads();
-  col_store<A, E, NT>(B.action + e0 * A, s_act, nvalid);
-  if (want_torque) col_store<9, E, NT>(B.applied_torque + e0 * 9, s_tq, nvalid);
+  if (full_tile) {
+    fence_async_proxy();           // generic-proxy writes to the slabs -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(B.action + e0 * A, s_act, sizeof(float) * E * A);
+      if (want_torque) bulk_store(B.applied_torque + e0 * 9, s_tq, sizeof(float) * E * 9);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else if (live) {
+#pragma unroll
+    for (int c = 0; c < A; ++c) B.action[e * A + c] = act[c];
+    if (want_torque) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) B.applied_torque[e * 9 + c] = s_tq[tid * 9 + c];
+    }
+  }
 
   // ---- ordered id lists (env_base.py:374-379; trifinger_env.py:413-416, :435-436) ---------------
   if (!need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
@@ -796,6 +858,8 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     B.goal_reset_ids[j] = e;
     if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
   }
+  // shared memory must outlive the bulk stores that read it
+  if (full_tile && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // standalone compaction (torch.nonzero(mask).view(-1))
@@ -1003,7 +1067,7 @@ int validate(const LgParams* P, const LgSimState* S, const LgBuffers* B, bool ne
   if (need_states && P->asymmetric_obs && (!B->states || !S->dof_force || !S->ft_sensors))
     return fail(LG_ERR_BAD_ARG, "asymmetric_obs needs states, dof_force and ft_sensors");
   const void* al[] = {S->dof_state, S->dof_force, S->ft_sensors, B->obs, B->states, B->obs_clipped, B->states_clipped,
-                      B->action, B->goal_pose, B->history};
+                      B->action, B->goal_pose, B->history, B->applied_torque};
   for (const void* p : al)
     if (p && !aligned16(p)) return fail(LG_ERR_BAD_ARG, "tensor base pointers must be 16-byte aligned");
   return LG_OK;
