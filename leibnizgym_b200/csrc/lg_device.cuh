@@ -177,14 +177,7 @@ struct DrawSource {
   __device__ __forceinline__ U4 block(uint32_t b) const {
     return philox4x32_10(U4{env_lo, env_hi_purpose, b, epoch_lo}, k0, k1);
   }
-  // canonical uniform column (include/leibniz_b200.h: LG_INJECT_U_COLS)
-  __device__ __forceinline__ float uniform(int col) const {
-    if (inj_u) return inj_u[col];
-    const U4 r = block((uint32_t)(col >> 2));
-    const uint32_t w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
-    return u01(w);
-  }
-  // canonical uniform columns 4b .. 4b+3 with ONE Philox evaluation
+  // canonical uniform columns 4b .. 4b+3 (include/leibniz_b200.h: LG_INJECT_U_COLS) with ONE Philox evaluation
   __device__ __forceinline__ void uniform4(int b, float out[4]) const {
     if (inj_u) {
       const float* p = inj_u + 4 * b;

@@ -3,9 +3,9 @@
 // Two launches per env step, both env-major and HBM-bound (no tensor cores: the path is
 // elementwise, ~2 FLOP/B):
 //   pre_physics_kernel   ordered mask compaction (decoupled look-back) + reset / goal-reset
-//                        sampling and scatter + action store + action->torque
+//                        sampling and scatter + action store + action->torque; tile slabs by TMA bulk copy
 //   post_physics_kernel  obs/states fill + scale_transform, six reward terms, termination,
-//                        step counters / timeouts / dones, episode statistics
+//                        step counters / timeouts / dones, episode statistics; one lane per output column
 // Reference paths are relative to /root/reference/leibnizgym/.
 #include <cuda_runtime.h>
 
@@ -84,54 +84,6 @@ __host__ __device__ inline void compute_coefs(const LgParams& P, double T, float
   c[C_NOISE_EPOCH] = bits.f;
 }
 static_assert(C_COUNT <= LG_NUM_COEF, "LgCoef too small");
-
-// Staging scheme of both kernels.  A tile slab is [E envs] x [C columns].  Each thread owns ONE
-// column and walks over envs with a fixed stride, so that
-//   * every address is base + compile-time offset: no per-element division or table lookup
-//     (the first version spent ~4400 instructions per warp, 3/4 of them index arithmetic, and was
-//     issue-bound at 20 us);
-//   * consecutive lanes touch consecutive floats of a row (coalesced 128-byte requests; for
-//     the contiguous buffers consecutive env groups are adjacent in memory as well);
-//   * all loads of a tile are issued into registers before the first one is consumed
-//     (memory-level parallelism is what bounds a one-wave, ~100-envs-per-SM kernel).
-template <int C, int E, int NT>
-struct ColSlab {
-  static constexpr int G = NT / C;                 // env groups that fit across the CTA
-  static constexpr int ACTIVE = G * C;             // threads that own a column
-  static constexpr int ITERS = (E + G - 1) / G;
-  static_assert(G >= 1, "tile narrower than a row");
-  float v[ITERS];
-  int col, grp;
-  bool on;
-  __device__ __forceinline__ ColSlab() : col(threadIdx.x % C), grp(threadIdx.x / C), on(threadIdx.x < ACTIVE) {}
-  // number of envs this thread visits: grp, grp+G, ... < nvalid
-  __device__ __forceinline__ int trips(int nvalid) const { return on ? (nvalid - grp + G - 1) / G : 0; }
-  // src_t: address of (env = grp, this thread's source column); row_stride in floats
-  __device__ __forceinline__ void load(const float* __restrict__ src_t, int row_stride, int nvalid) {
-    const int n = trips(nvalid);
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it)
-      if (it < n) v[it] = ld_stream1(src_t + (int64_t)(it * G) * row_stride);
-  }
-  // dst_t: shared address of (env = grp, destination column)
-  __device__ __forceinline__ void drain(float* dst_t, int row_stride, int nvalid) {
-    const int n = trips(nvalid);
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it)
-      if (it < n) dst_t[it * G * row_stride] = v[it];
-  }
-};
-
-// contiguous [E, C] slab: shared tile -> global, thread-per-column
-template <int C, int E, int NT>
-__device__ __forceinline__ void col_store(float* __restrict__ dst_tile, const float* src_tile, int nvalid) {
-  ColSlab<C, E, NT> w;
-  float* dst = dst_tile + w.grp * C + w.col;
-  const float* src = src_tile + w.grp * C + w.col;
-#pragma unroll
-  for (int it = 0; it < w.ITERS; ++it)
-    if (w.on && w.grp + it * w.G < nvalid) dst[it * w.G * C] = src[it * w.G * C];
-}
 
 // Fast division by a per-column constant: q = x*r, q' = fma(fma(-q, span, x), r, q) with r = fp32(1/span)
 // correctly rounded (Markstein).  Contract, verified exhaustively by lg_selftest_division over all 2^32
