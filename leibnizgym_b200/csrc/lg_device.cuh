@@ -29,7 +29,7 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
 }
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
