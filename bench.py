@@ -348,12 +348,12 @@ def run_gpu(args, wl):
 def run_e2e(args, wl, cfg, dev, rank, world):
     """Public-API step (VecTaskPython.step + get_state) with HOST-resident simulator state, action and
     results, every step.  Three transports (--e2e-mode):
-      zc      (default) zero copy: the simulator tensors and the action sit in pinned host memory and the
+      zc      zero copy: the simulator tensors and the action sit in pinned host memory and the
               fused kernels read the rows they need — and write obs/states/reward/dones — over PCIe themselves;
       zc_out  inputs staged by host->device copies of the five simulator tensors, results written to the host
               by the kernels;
-      copy    (default) inputs staged by host->device copies (of the rigid-body tensor only the run of bodies
-              that holds the fingertips), results copied back with four device->host copies."""
+      copy    (default) inputs staged by host->device copies (of root_state / rigid_body only the object and
+              fingertip rows), results copied back with four device->host copies."""
     import torch.distributed as dist
 
     from leibnizgym_b200.env import TrifingerEnv
@@ -410,14 +410,16 @@ def run_e2e(args, wl, cfg, dev, rank, world):
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    bodies = 20 if args.e2e_full_upload else 11   # rigid bodies staged per env (fingertips are bodies 6, 11, 16)
-    full_h2d = 4 * N * (18 + 4 * 13 + bodies * 13 + 9 + 18 + 9)
+    # rows staged per env: everything with --e2e-full-upload, else the object actor's root row and the 3 fingertip bodies
+    root_rows, body_rows = (4, 20) if args.e2e_full_upload else (1, 3)
+    full_h2d = 4 * N * (18 + root_rows * 13 + body_rows * 13 + (9 + 18 if asym else 0) + 9)
     # zero copy: bytes the kernels fetch from host memory = the rows the path reads (dof_state twice: torque + obs)
     zc_h2d = 4 * N * (9 + 18 + 18 + 13 + 39 + (9 + 18 if asym else 0))
-    d2h = 4 * N * (obs_dim + st_dim + 1 + (0 if mode == "copy" else 9)) + N   # zero-copy modes also return the torque
+    shared_obs = bool(chunks) and vec._pipeline.shared_obs   # obs = first columns of the downloaded states
+    d2h = 4 * N * ((0 if shared_obs else obs_dim) + st_dim + 1 + (0 if mode == "copy" else 9)) + N   # zero-copy modes also return the torque
     return {"value": steps * N * world / (ms * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": zc_h2d if mode == "zc" else full_h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": ms / steps, "mode": mode, "pipeline_chunks": chunks,
+            "steps": steps, "ms_per_step": ms / steps, "mode": mode, "pipeline_chunks": chunks, "obs_is_view_of_states": shared_obs,
             "api": "VecTaskPython.step + get_state; simulator state, action and results in pinned host memory"}
 
 
@@ -432,7 +434,7 @@ def main():
     ap.add_argument("--ring", type=int, default=32, help="distinct simulator states in HBM")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-mode", default="copy", choices=["zc", "zc_out", "copy"])
-    ap.add_argument("--e2e-chunks", type=int, default=2, help="env ranges of the host pipeline (0 = un-chunked copies)")
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="env ranges of the host pipeline (0 = un-chunked copies)")
     ap.add_argument("--e2e-full-upload", action="store_true", help="upload all 20 rigid bodies, not just the fingertip run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")

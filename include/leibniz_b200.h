@@ -298,11 +298,13 @@ typedef struct LgHostStep {
   const float* dof_state_host; const float* root_state_host; const float* rigid_body_host;
   const float* dof_force_host; const float* ft_sensors_host; const float* action_host;
   float* obs_host; float* states_host; float* reward_host; uint8_t* dones_host;
+  /* obs_host may be NULL when asymmetric_obs && !dr_activate: the observation is then the first obs_dim columns
+     of every states_host row (same values; ref trifinger_env.py:995-1051) and is not transferred a second time */
   float* action_staging;    /* device [N, A] scratch for the uploaded action */
 } LgHostStep;
 /* Host -> device staging of one simulator state (pinned host pointers of H; outputs of H unused): the whole
- * dof_state / root_state / dof_force / ft_sensors tensors, and of rigid_body only the contiguous run of bodies
- * that contains the three fingertips (one strided 2-D copy; 11 of 20 bodies for the TriFinger). */
+ * dof_state / dof_force / ft_sensors tensors; of root_state only the object actor's rows and of rigid_body only
+ * the three fingertip bodies (strided 2-D copies of 52-byte rows) -- the rows lg_post_physics reads. */
 int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep* H, void* stream);
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B,
                  const LgHostStep* H, double sched_step, void* stream);

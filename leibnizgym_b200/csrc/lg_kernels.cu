@@ -1206,12 +1206,18 @@ int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep
   const int64_t N = P->num_envs;
   const cudaMemcpyKind k = cudaMemcpyHostToDevice;
   cudaMemcpyAsync(S->dof_state, H->dof_state_host, sizeof(float) * N * 18, k, st);
-  cudaMemcpyAsync(S->root_state, H->root_state_host, sizeof(float) * N * P->actors_per_env * 13, k, st);
-  // rigid bodies: only the contiguous run of bodies that contains the three fingertips (bodies 6..16 of 20)
-  int lo = P->fingertip_body[0], hi = P->fingertip_body[0];
-  for (int i = 1; i < 3; ++i) { lo = P->fingertip_body[i] < lo ? P->fingertip_body[i] : lo; hi = P->fingertip_body[i] > hi ? P->fingertip_body[i] : hi; }
-  const size_t pitch = sizeof(float) * 13 * P->bodies_per_env, width = sizeof(float) * 13 * (hi - lo + 1);
-  cudaMemcpy2DAsync(const_cast<float*>(S->rigid_body) + lo * 13, pitch, H->rigid_body_host + lo * 13, pitch, width, (size_t)N, k, st);
+  // Of root_state and rigid_body only the rows the path reads: the object actor's row and the three fingertip
+  // bodies, each one strided 2-D copy of 52-byte rows.  Measured on a B200 (PCIe 5 x16, scripts/pcie_probe.cu,
+  // 16384 envs): object rows 39 us against 65 us for the whole tensor; the three fingertip copies 143 us against
+  // 199 us for the run of bodies 6..16 and 311 us for the whole tensor.
+  const size_t row = sizeof(float) * 13;
+  cudaMemcpy2DAsync(S->root_state + (size_t)P->object_slot * 13, row * P->actors_per_env,
+                    H->root_state_host + (size_t)P->object_slot * 13, row * P->actors_per_env, row, (size_t)N, k, st);
+  const size_t pitch = row * P->bodies_per_env;
+  for (int i = 0; i < 3; ++i) {
+    const size_t off = (size_t)P->fingertip_body[i] * 13;
+    cudaMemcpy2DAsync(const_cast<float*>(S->rigid_body) + off, pitch, H->rigid_body_host + off, pitch, row, (size_t)N, k, st);
+  }
   if (P->asymmetric_obs) {
     if (!H->dof_force_host || !H->ft_sensors_host) return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
     cudaMemcpyAsync(const_cast<float*>(S->dof_force), H->dof_force_host, sizeof(float) * N * 9, k, st);
@@ -1224,9 +1230,10 @@ int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffe
                            double sched_step, int chunks, void* stream_main, void* stream_up, void* stream_down) {
   if (int rc = validate(P, S, B, true)) return rc;
   if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||
-      !H->obs_host || !H->reward_host)
+      !H->reward_host || (!H->obs_host && !(P->asymmetric_obs && H->states_host && !P->dr_activate)))
     return fail(LG_ERR_BAD_ARG, "null host buffer");
   if (chunks < 1 || chunks > 16) return fail(LG_ERR_BAD_ARG, "chunks must be in 1..16");
+  if (chunks == 1) return lg_step_host(P, S, B, H, sched_step, stream_main);   // nothing to overlap: one stream, no events
   if (P->asymmetric_obs && (!H->dof_force_host || !H->ft_sensors_host || !H->states_host))
     return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
   cudaStream_t main = (cudaStream_t)stream_main, up = (cudaStream_t)stream_up, down = (cudaStream_t)stream_down;
@@ -1279,7 +1286,7 @@ int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffe
     if (int rc = lg_post_physics(&pc, &sc, &bc, sched_step, stream_main)) return rc;
     cudaEventRecord(pool.post[c], main);
     cudaStreamWaitEvent(down, pool.post[c], 0);
-    cudaMemcpyAsync(H->obs_host + lo * od, obs_src + lo * od, sizeof(float) * (hi - lo) * od, cudaMemcpyDeviceToHost, down);
+    if (H->obs_host) cudaMemcpyAsync(H->obs_host + lo * od, obs_src + lo * od, sizeof(float) * (hi - lo) * od, cudaMemcpyDeviceToHost, down);
     if (sd) cudaMemcpyAsync(H->states_host + lo * sd, st_src + lo * sd, sizeof(float) * (hi - lo) * sd, cudaMemcpyDeviceToHost, down);
     cudaMemcpyAsync(H->reward_host + lo, B->reward + lo, sizeof(float) * (hi - lo), cudaMemcpyDeviceToHost, down);
     if (H->dones_host && B->dones) cudaMemcpyAsync(H->dones_host + lo, B->dones + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, down);
@@ -1293,8 +1300,10 @@ int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffe
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {
   if (int rc = validate(P, S, B, true)) return rc;
   if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||
-      !H->obs_host || !H->reward_host)
+      !H->reward_host || (!H->obs_host && !(P->asymmetric_obs && H->states_host && !P->dr_activate)))
     return fail(LG_ERR_BAD_ARG, "null host buffer");
+  if (P->asymmetric_obs && (!H->dof_force_host || !H->ft_sensors_host || !H->states_host))
+    return fail(LG_ERR_BAD_ARG, "null host buffer (asymmetric)");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = P->num_envs;
   const int obs_dim = 32 + P->action_dim, state_dim = obs_dim + 72;
@@ -1305,7 +1314,7 @@ int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, con
   if (int rc = lg_upload_sim_state(P, S, H, stream)) return rc;
   if (int rc = lg_post_physics(P, S, B, sched_step, stream)) return rc;
   const float* obs_src = B->obs_clipped ? B->obs_clipped : B->obs;
-  cudaMemcpyAsync(H->obs_host, obs_src, sizeof(float) * N * obs_dim, cudaMemcpyDeviceToHost, st);
+  if (H->obs_host) cudaMemcpyAsync(H->obs_host, obs_src, sizeof(float) * N * obs_dim, cudaMemcpyDeviceToHost, st);
   if (P->asymmetric_obs) {
     const float* st_src = B->states_clipped ? B->states_clipped : B->states;
     cudaMemcpyAsync(H->states_host, st_src, sizeof(float) * N * state_dim, cudaMemcpyDeviceToHost, st);

@@ -476,14 +476,17 @@ class TrifingerEnv(IsaacEnvBase):
         """`_step_info` of the reference (trifinger_env.py:554, :1068, :1076, :1099) as 0-d fp64 views
         of the per-step statistics buffer: valid until the next step overwrites them; values are
         this shard's (see global_step_info)."""
-        buf, info = self._step_stats, {}
-        for i, name in enumerate(nat.TERM_NAMES):
-            if self.config["reward_terms"].get(name, {}).get("activate"):
-                info[f"env/rewards/{name}"] = buf[i]
-        info["env/current_position_goal/count"] = buf[nat.STAT_POSITION_GOAL]
-        info["env/current_orientation_goal/count"] = buf[nat.STAT_ORIENTATION_GOAL]
-        info["env/average_consecutive_success"] = buf[nat.STAT_SUCCESSES]
-        return info
+        views = getattr(self, "_info_views", None)
+        if views is None or views[0] is not self._step_stats:   # the views never change: build them once
+            buf, info = self._step_stats, {}
+            for i, name in enumerate(nat.TERM_NAMES):
+                if self.config["reward_terms"].get(name, {}).get("activate"):
+                    info[f"env/rewards/{name}"] = buf[i]
+            info["env/current_position_goal/count"] = buf[nat.STAT_POSITION_GOAL]
+            info["env/current_orientation_goal/count"] = buf[nat.STAT_ORIENTATION_GOAL]
+            info["env/average_consecutive_success"] = buf[nat.STAT_SUCCESSES]
+            views = self._info_views = (buf, info)
+        return dict(views[1])
 
     def global_step_info(self) -> Dict[str, float]:
         """Whole-job statistics: all-reduces the 16 shard sums (the only cross-GPU traffic of the
