@@ -287,6 +287,11 @@ int lg_selftest_division(float span, float rcp, unsigned long long* out_dev, voi
 /* Extension (no reference code): world-frame cube corners, [n,7] poses -> [n,8,3] keypoints. */
 int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n, void* stream);
 
+/* Extension (stand-in for PhysX integrating the moving-goal task's goal body): advances the goal
+ * actor's root rows of S->root_state by dt -- p += v dt, q <- normalize(exp(w dt / 2) (x) q), w = world-frame
+ * angular velocity (cols 10:13, re-imposed each step by lg_pre_physics / lg_pre_step, trifinger_env.py:1267-1277). */
+int lg_integrate_goal(const LgParams* P, const LgSimState* S, float dt, void* stream);
+
 /*
  * Host-buffer convenience entry for callers whose simulator state lives in HOST memory
  * (the reference's default `use_gpu_pipeline: False`, env_base.py:60): copies the five

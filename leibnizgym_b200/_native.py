@@ -116,6 +116,7 @@ SYMBOLS = {
     "lg_saturate": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "lg_lgsk_kernel": (C.c_int, [_vp, C.c_float, _vp, _i64, _vp]),
     "lg_cube_keypoints": (C.c_int, [_vp, C.c_float, _vp, _i64, _vp]),
+    "lg_integrate_goal": (C.c_int, [_P, _S, C.c_float, _vp]),
     "lg_selftest_division": (C.c_int, [C.c_float, C.c_float, _vp, _vp]),
     "lg_upload_sim_state": (C.c_int, [_P, _S, C.POINTER(LgHostStep), _vp]),
     "lg_step_host_pipelined": (C.c_int, [_P, _S, _B, C.POINTER(LgHostStep), C.c_double, C.c_int, _vp, _vp, _vp]),

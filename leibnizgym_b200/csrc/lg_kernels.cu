@@ -335,6 +335,17 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     }
     if (dcol >= 0 && !(amax < kDivSafeMax))  // cold: same addresses, same thread: plain overwrite
       output_exact<L::STATE, L::OBS, ASYM>(P, B, src, stride, cnt, e0 + env_first, dcol);
+    // moving goal (__update_goal_movement_post, trifinger_env.py:1279-1284): after the rewards, the goal pose
+    // buffer takes the pose the simulator integrated for the goal body.  The goal-role lanes own their elements
+    // of goal_pose (read above, overwritten here), so no other lane observes the change within this step.
+    if (EXT && REWARD && P.goal_rotation && front && role >= 25 && role < 32) {
+      const int c = role - 25, actor_stride = P.actors_per_env * 13;
+      const float* g_src = S.root_state + ((e0 + env_first) * P.actors_per_env + P.goal_slot) * 13 + c;
+      float* g_dst = B.goal_pose + (e0 + env_first) * 7 + c;
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (FULLC || k < cnt) g_dst[k * 7] = g_src[(int64_t)k * actor_stride];
+    }
   };
   // ======== reward warps: lane = env, warp = sub-task (uniform control flow inside a warp) ================
   if (REWARD && rw < 4) {
@@ -770,6 +781,13 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   // ---- resets (cold) -------------------------------------------------------------------------------
   if (f_reset || f_goal)
     reset_cold(P, S, B, e, f_reset, f_goal, (int64_t)ex_a + t.rank_a, (int64_t)ex_b + t.rank_b, (uint64_t)epoch);
+  // ---- moving goal (__update_goal_movement_pre, trifinger_env.py:1267-1277): every step the goal body's
+  // angular velocity is re-imposed from the movement buffer (freshly sampled above for envs that reset)
+  if (P.goal_rotation && live) {
+    float* row = S.root_state + (P.actors_per_env * e + P.goal_slot) * 13;
+    const float* gm = B.goal_movement + e * 6;
+    row[10] = gm[3]; row[11] = gm[4]; row[12] = gm[5];
+  }
   // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
   if (want_torque && live) {
     const bool dof_rewritten = f_reset && P.robot_reset != LG_RESET_NONE;
@@ -880,6 +898,11 @@ __global__ void pre_step_kernel(const __grid_constant__ LgParams P, const LgSimS
   float act[LG_MAX_ACTION_DIM];
   for (int c = 0; c < P.action_dim; ++c) act[c] = B.action[e * P.action_dim + c];
   torque_one_env(P, act, S.dof_state + e * 18, B.applied_torque + e * 9);
+  if (P.goal_rotation) {  // __update_goal_movement_pre (trifinger_env.py:1267-1277)
+    float* row = S.root_state + (P.actors_per_env * e + P.goal_slot) * 13;
+    const float* gm = B.goal_movement + e * 6;
+    row[10] = gm[3]; row[11] = gm[4]; row[12] = gm[5];
+  }
 }
 
 // ---- batched primitives -------------------------------------------------------------------------
@@ -921,6 +944,26 @@ __global__ void keypoints_kernel(const float* pose, float size, float* out, int6
   float rx, ry, rz;
   quat_rotate(Quat{p[3], p[4], p[5], p[6]}, vx, vy, vz, rx, ry, rz);
   out[i * 3] = p[0] + rx; out[i * 3 + 1] = p[1] + ry; out[i * 3 + 2] = p[2] + rz;
+}
+
+// Stand-in for the simulator's rigid-body integration of the (gravity-free, collision-free) goal body of the
+// moving-goal task: semi-implicit Euler over dt on root rows [n, 13] = pos 3 | quat xyzw 4 | lin vel 3 | ang vel 3,
+//   p += v dt;   q <- normalize(exp(w dt / 2) (x) q)   (world-frame angular velocity, quaternion exponential).
+__global__ void integrate_rows_kernel(float* rows, int64_t row_stride, float dt, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* r = rows + i * row_stride;
+  const float wx = r[10], wy = r[11], wz = r[12];
+  r[0] = r[0] + r[7] * dt; r[1] = r[1] + r[8] * dt; r[2] = r[2] + r[9] * dt;
+  const float w = norm3(wx, wy, wz);
+  if (!(w > 0.0f)) return;   // not turning: the orientation stays bit-identical
+  const float half = 0.5f * w * dt;
+  const float k = w > 1e-12f ? __fdiv_rn(sinf(half), w) : 0.5f * dt;   // sin(half)/w -> dt/2 as w -> 0
+  const Quat dq{wx * k, wy * k, wz * k, cosf(half)};
+  Quat q = quat_mul(dq, Quat{r[3], r[4], r[5], r[6]});
+  const float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  const float inv = __frcp_rn(fmaxf(nrm, 1e-12f));
+  r[3] = q.x * inv; r[4] = q.y * inv; r[5] = q.z * inv; r[6] = q.w * inv;
 }
 
 // exhaustive check of div_by_const's contract for one (span, rcp): all 2^32 numerators.
@@ -1047,8 +1090,8 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
   const int E = P->action_dim == 9 ? pick_tile_envs(P->num_envs) : 32;
   const unsigned grid = (unsigned)((P->num_envs + E - 1) / E);
   cudaError_t err;
-  // extensions (DR noise, keypoint term) live in their own instantiation: switched off they cost nothing
-  const bool ext = P->dr_activate || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1);
+  // rarely-used paths (DR noise, keypoint term, moving goal) live in their own instantiation: switched off they cost nothing
+  const bool ext = P->dr_activate || P->goal_rotation || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1);
 #define LG_K(AD, AS, CL, EE) (ext ? launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, true>, grid, lg::kPostThreads, st, *P, *S, *B, cf) \
                                   : launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, false>, grid, lg::kPostThreads, st, *P, *S, *B, cf))
 #define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))
@@ -1193,6 +1236,13 @@ int lg_cube_keypoints(const float* pose, float cube_size, float* out, int64_t n,
   return check_launch("keypoints_kernel");
 }
 
+int lg_integrate_goal(const LgParams* P, const LgSimState* S, float dt, void* stream) {
+  if (!P || !S || !S->root_state || P->num_envs < 0) return fail(LG_ERR_BAD_ARG, "bad argument");
+  const int64_t n = P->num_envs;
+  if (n) lg::integrate_rows_kernel<<<LG_GRID(n)>>>(S->root_state + (size_t)P->goal_slot * 13, (int64_t)P->actors_per_env * 13, dt, n);
+  return check_launch("integrate_rows_kernel");
+}
+
 int lg_selftest_division(float span, float rcp, unsigned long long* mismatches_dev, void* stream) {
   if (!mismatches_dev) return fail(LG_ERR_BAD_ARG, "null argument");
   lg::selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(span, rcp, mismatches_dev);
@@ -1213,6 +1263,9 @@ int lg_upload_sim_state(const LgParams* P, const LgSimState* S, const LgHostStep
   const size_t row = sizeof(float) * 13;
   cudaMemcpy2DAsync(S->root_state + (size_t)P->object_slot * 13, row * P->actors_per_env,
                     H->root_state_host + (size_t)P->object_slot * 13, row * P->actors_per_env, row, (size_t)N, k, st);
+  if (P->goal_rotation)  // moving goal: the pose the simulator integrated for the goal body is read back (:1279-1284)
+    cudaMemcpy2DAsync(S->root_state + (size_t)P->goal_slot * 13, row * P->actors_per_env,
+                      H->root_state_host + (size_t)P->goal_slot * 13, row * P->actors_per_env, sizeof(float) * 7, (size_t)N, k, st);
   const size_t pitch = row * P->bodies_per_env;
   for (int i = 0; i < 3; ++i) {
     const size_t off = (size_t)P->fingertip_body[i] * 13;

@@ -466,6 +466,7 @@ class TrifingerEnv(IsaacEnvBase):
         nat.check(self._lib.lg_pre_physics(self._P, self._S, self._B, action.data_ptr(), self._stream()), "lg_pre_physics")
         self._clear_injection()
         self._sim.set_dof_actuation_force_tensor(self._applied_torque)
+        self._notify_goal_movement()
         for _ in range(self.control_decimation):
             self._simulate()
         self._call("lg_post_physics", self._P, self._S, self._B, float(self.env_steps_count))
@@ -517,6 +518,17 @@ class TrifingerEnv(IsaacEnvBase):
     def _pre_step(self):
         self._call("lg_pre_step", self._P, self._S, self._B)
         self._sim.set_dof_actuation_force_tensor(self._applied_torque)
+        self._notify_goal_movement()
+
+    def _notify_goal_movement(self):
+        """Moving goal (ref trifinger_env.py:1267-1277): the kernels re-imposed every goal body's angular velocity;
+        tell the simulator which root rows changed (all goal actors, every step)."""
+        if self._P.goal_rotation:
+            if getattr(self, "_all_goal_indices", None) is None:
+                apa, slot = self._sim.actors_per_env, self._sim.slots[2]
+                self._all_goal_indices = (torch.arange(self.num_instances, device=self._torch_device, dtype=torch.int32)
+                                          * apa + slot)
+            self._sim.set_actor_root_state_tensor_indexed(self._all_goal_indices, self.num_instances)
 
     def _post_step(self):
         self._P.fuse_bookkeeping = 0

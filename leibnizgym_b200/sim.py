@@ -40,6 +40,7 @@ class SyntheticSim:
         self.before_simulate: Optional[Callable[["SyntheticSim"], None]] = None  # test hook
         self.applied_torque = None
         self._uploader = None
+        self._integrate = None
         self._load(0)  # what refresh_* shows before the first simulate
 
     def _load(self, t: int) -> None:
@@ -74,11 +75,33 @@ class SyntheticSim:
                       "lg_upload_sim_state")
         self._uploader = upload
 
+    def enable_goal_integration(self, params, dt: float) -> None:
+        """Moving-goal task (ref trifinger_env.py:947, :1267-1284): instead of taking the goal actor's root rows from
+        the sequence, integrate them like a simulator would (lg_integrate_goal: p += v dt, q <- exp(w dt/2) q), so
+        the goal really rotates with the angular velocity the env imposes each step."""
+        from . import _native as nat
+        lib = nat.load()
+        S = nat.LgSimState(*(x.data_ptr() for x in (self.dof_state, self.root_state, self.rigid_body,
+                                                     self.dof_force, self.ft_sensors)))
+        goal_rows = self.root_state.view(self.num_envs, self.actors_per_env, 13)[:, self.slots[2]]
+
+        def integrate(load):
+            keep = goal_rows.clone()
+            load()
+            goal_rows.copy_(keep)
+            nat.check(lib.lg_integrate_goal(params, S, float(dt), torch.cuda.current_stream(self.device).cuda_stream),
+                      "lg_integrate_goal")
+        self._integrate = integrate
+
     # -- the slice of the gym API the path uses ---------------------------------------
     def simulate(self) -> None:
         if self.before_simulate is not None:
             self.before_simulate(self)
-        self._load(self.cursor % self.seq.num_steps)
+        t = self.cursor % self.seq.num_steps
+        if self._integrate is not None:
+            self._integrate(lambda: self._load(t))
+        else:
+            self._load(t)
         self.cursor += 1
         self.frame_count += 1
 

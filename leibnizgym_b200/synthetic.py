@@ -110,6 +110,21 @@ def make_sequence(seed: int, num_steps: int, num_envs: int, device: str = "cpu",
     return StateSequence(dof_state, root_state, rigid_body.contiguous(), dof_force, ft_sensors, action)
 
 
+def plant_goal_rows(seq: StateSequence, seed: int) -> None:
+    """Fill the goal actor's root rows of every step with a seeded random pose (position inside the arena, unit
+    quaternion) and angular velocity: what a simulator that integrates a moving goal body would leave there."""
+    T, N = seq.num_steps, seq.num_envs
+    dev = seq.root_state.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed) * 7919 + 17)
+    kw = dict(generator=g, device=dev, dtype=torch.float32)
+    goal = seq.root_state.view(T, N, NUM_ACTORS, ROW)[:, :, GOAL_SLOT]
+    goal[..., 0:2] = -0.12 + 0.24 * torch.rand(T, N, 2, **kw)
+    goal[..., 2] = 0.0325 + 0.1 * torch.rand(T, N, **kw)
+    goal[..., 3:7] = _unit_quat(g, (T, N), dev)
+    goal[..., 10:13] = 0.5 * torch.randn(T, N, 3, **kw)
+
+
 def plant_edge_cases(seq: StateSequence, goal_pose: torch.Tensor, first_step: int = 1) -> None:
     """Overwrite the first envs of every step >= first_step with the edge cases of SURVEY.md §A.7.
 

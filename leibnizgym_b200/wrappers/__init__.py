@@ -1,3 +1,4 @@
+from .rlg_adapter import RlGamesGpuEnvAdapter
 from .vec_task import VecTask, VecTaskPython
 
-__all__ = ["VecTask", "VecTaskPython"]
+__all__ = ["VecTask", "VecTaskPython", "RlGamesGpuEnvAdapter"]

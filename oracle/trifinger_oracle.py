@@ -587,6 +587,7 @@ class OracleEnv:
         self.applied_torque = applied
         if cfg["goal_movement"]["rotation"]["activate"]:  # ref :1267-1277
             self.sim.root[self.idx_goal, 10:13] = self.goal_movement[:, 3:6]
+            self.index_lists["root_move"] = self.idx_goal.to(torch.int32)
 
     # -- observations / states (ref trifinger_env.py:959-1051) -----------------------
     def fill_observations_and_states(self):

@@ -24,6 +24,34 @@ __global__ void gather_kernel(const float* __restrict__ dof, const float* __rest
   }
 }
 
+
+// rows only: the object root row and the three fingertip rows of each env (4 x 13 floats), read from host memory
+__global__ void gather_rows(const float* __restrict__ root, const float* __restrict__ body,
+                            float* __restrict__ d_root, float* __restrict__ d_body, int N) {
+  const long long total = (long long)N * 52;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int env = (int)(i / 52), c = (int)(i % 52), k = c / 13, j = c % 13;
+    if (k == 0) d_root[(env * 4 + 2) * 13 + j] = root[(env * 4 + 2) * 13 + j];
+    else { const int b = 1 + 5 * k; d_body[(env * 20 + b) * 13 + j] = body[(env * 20 + b) * 13 + j]; }
+  }
+}
+// same rows, fetched as whole 32-byte sectors: lane group of 4 x float4... here 8 lanes x float per sector
+__global__ void gather_rows_sectors(const float* __restrict__ root, const float* __restrict__ body,
+                                    float* __restrict__ d_root, float* __restrict__ d_body, int N) {
+  // each row (52 B at a 4-byte-aligned address) is covered by 3 aligned 32-byte sectors = 24 floats; 24 lanes per row
+  const long long total = (long long)N * 4 * 24;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / 24; const int l = (int)(i % 24);
+    const int env = (int)(r >> 2), k = (int)(r & 3);
+    const float* src = k == 0 ? root + (env * 4 + 2) * 13 : body + (env * 20 + 1 + 5 * k) * 13;
+    float* dst = k == 0 ? d_root + (env * 4 + 2) * 13 : d_body + (env * 20 + 1 + 5 * k) * 13;
+    const long long base = ((long long)(size_t)src & ~31ll);
+    const float* p = (const float*)base + l;
+    const long long off = p - src;
+    if (off >= 0 && off < 13) dst[off] = *p;
+  }
+}
+
 // flat float4 copy from host-mapped memory (upper bound for zero-copy reads)
 __global__ void zc_copy(const float4* __restrict__ src, float4* __restrict__ dst, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -148,6 +176,24 @@ int main(int argc, char** argv) {
     cudaEventRecord(b, st); CK(cudaEventSynchronize(b));
     cudaEventElapsedTime(&ms, a, b);
     printf("download split over 2 streams: %.1f us\n", ms / R * 1000.f);
+  }
+  {
+    cudaEvent_t a, b, e2; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventCreate(&e2);
+    for (int blocks : {148, 592, 2368}) {
+      printf("gather rows only (208 B/env) grid %d: %.1f us\n", blocks, timeit(st, R, [&] { gather_rows<<<blocks, 256, 0, st>>>(h_root, h_body, d_root, d_body, N); }));
+      printf("gather rows by sectors grid %d: %.1f us\n", blocks, timeit(st, R, [&] { gather_rows_sectors<<<blocks, 256, 0, st>>>(h_root, h_body, d_root, d_body, N); }));
+    }
+    cudaDeviceSynchronize();
+    cudaEventRecord(a, st);
+    for (int i = 0; i < R; ++i) {
+      cudaEventRecord(e2, st); cudaStreamWaitEvent(st2, e2, 0);
+      small();
+      gather_rows<<<592, 256, 0, st2>>>(h_root, h_body, d_root, d_body, N);
+      cudaEventRecord(e2, st2); cudaStreamWaitEvent(st, e2, 0);
+    }
+    cudaEventRecord(b, st); CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("small DMA || gather rows: %.1f us\n", ms / R * 1000.f);
   }
   return 0;
 }

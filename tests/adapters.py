@@ -79,6 +79,8 @@ class OracleAdapter:
             return _np(e.index_lists["root_reset"] if "root_reset" in e.index_lists else e.index_lists["root_goal"])
         if key == "root_index_list1":
             return _np(e.index_lists["root_goal"])
+        if key == "root_index_list_move":
+            return _np(e.index_lists["root_move"])
         if key == "applied_torque":
             return _np(e.applied_torque)
         if key == "goal_pose":
@@ -119,12 +121,16 @@ class CudaAdapter:
         self.N = config["num_instances"]
         self.sim = SyntheticSim(seq.to(device), device=device)
         self.sim.before_simulate = self._capture
+        self.sim.set_actor_root_state_tensor_indexed = self._root_indexed   # record what the simulator is told
         self.env = TrifingerEnv(config=config, device=device, verbose=False, sim=self.sim)
         self.env.enable_term_rewards(True)
         self.fused = fused
         self.k_reset = self.N
         self.k_goal = 0
         self._ids = (torch.arange(self.N), torch.zeros(0, dtype=torch.long))
+
+    def _root_indexed(self, indices, count):
+        self.sim.last_root_indexed = indices[:int(count)].clone()
 
     def _capture(self, sim):
         self.pre_sim_dof = sim.dof_state.clone()
@@ -191,6 +197,8 @@ class CudaAdapter:
             return _np(e._reset_root_indices[:3 * kr] if kr else e._goal_root_indices[:kg])
         if key == "root_index_list1":
             return _np(e._goal_root_indices[:kg])
+        if key == "root_index_list_move":
+            return _np(self.sim.last_root_indexed)
         if key == "applied_torque":
             return _np(e._applied_torque)
         if key == "goal_pose":

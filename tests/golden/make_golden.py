@@ -32,7 +32,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, HERE)
 
 from leibnizgym_b200.synthetic import (bernoulli_masks, make_sequence, plant_edge_cases,  # noqa: E402
-                                       FINGERTIP_BODIES)
+                                       plant_goal_rows, FINGERTIP_BODIES)
 from scenarios import SCENARIOS  # noqa: E402
 
 U_COLS, N_COLS = 24, 8
@@ -81,14 +81,18 @@ def canonical_draws(log, cfg, k, goal_only):
 
 
 def run_scenario(name: str, record_draws: bool) -> dict:
-    from ref_harness import DrawRecorder, build_reference_env, reward_terms_of
+    from ref_harness import DrawRecorder, build_reference_env, reward_terms_of, stash_goal_before_movement
     sc = SCENARIOS[name]
     N, T, seed = sc["N"], sc["T"], sc["seed"]
     seq = make_sequence(seed, T, N)
     reset_masks = bernoulli_masks(seed, T, N, sc.get("reset_p", 0.0))
     goal_masks = bernoulli_masks(seed + 1, T, N, sc.get("goal_reset_p", 0.0))
+    if sc.get("plant_goal_rows"):   # what a simulator integrating the goal body would leave in its root rows
+        plant_goal_rows(seq, seed)
     env, fake = build_reference_env(sc["config"], seq)
     cfg = env.config
+    if cfg["goal_movement"]["rotation"]["activate"]:
+        stash_goal_before_movement(env)
     out = {"meta": dict(name=name, N=N, T=T, seed=seed, torch=torch.__version__,
                         config=json.loads(json.dumps(sc["config"])))}
     steps = []
@@ -144,7 +148,10 @@ def run_scenario(name: str, record_draws: bool) -> dict:
             s["pre_sim_obj_root"] = fake.pre_sim_root.view(N, 4, 13)[:, 2].numpy().copy()
             s["pre_sim_goal_root"] = fake.pre_sim_root.view(N, 4, 13)[:, 3].numpy().copy()
             s["dof_index_list"] = None if fake.dof_indexed is None else fake.dof_indexed.numpy()
-            s["root_index_lists"] = [x.numpy() for x in fake.root_indexed]
+            lists = [x.numpy() for x in fake.root_indexed]
+            if cfg["goal_movement"]["rotation"]["activate"]:   # the last call of the step is __update_goal_movement_pre's
+                s["root_index_list_move"], lists = lists[-1], lists[:-1]
+            s["root_index_lists"] = lists
             s["applied_torque"] = fake.applied_torque.numpy().copy()
             s["goal_pose"] = env._object_goal_poses_buf.numpy().copy()
             s["goal_movement"] = env._object_goal_movement_buf.numpy().copy()
@@ -168,6 +175,7 @@ def run_scenario(name: str, record_draws: bool) -> dict:
         action=seq.action.numpy(),
         reset_masks=None if reset_masks is None else reset_masks.numpy(),
         goal_masks=None if goal_masks is None else goal_masks.numpy(),
+        goal_root=seq.root_state.view(T, N, 4, 13)[:, :, 3].numpy().copy() if sc.get("plant_goal_rows") else None,
     )
     return out
 

@@ -212,6 +212,17 @@ def build_reference_env(config: dict, seq, quiet: bool = True):
     return env, fake
 
 
+def stash_goal_before_movement(env):
+    """Moving-goal scenarios: keep a copy of the goal pose the reward terms saw, by wrapping the (name-mangled)
+    post-movement hook on the instance.  The reference's behaviour is unchanged."""
+    inner = env._TrifingerEnv__update_goal_movement_post
+
+    def wrapped():
+        env._goal_pose_used_by_rewards = env._object_goal_poses_buf.clone()
+        inner()
+    env._TrifingerEnv__update_goal_movement_post = wrapped
+
+
 def reward_terms_of(env):
     """Re-evaluates the six terms on the histories the last `_post_step` used -> [6, N]."""
     t = env._reward_terms
@@ -219,7 +230,8 @@ def reward_terms_of(env):
     T = env.env_steps_count
     ft0, ft1 = env._fingertips_frames_state_history[0], env._fingertips_frames_state_history[1]
     ob0, ob1 = env._object_state_history[0], env._object_state_history[1]
-    goal = env._object_goal_poses_buf
+    # moving goal: the terms were evaluated BEFORE __update_goal_movement_post replaced the goal pose (ref :559)
+    goal = getattr(env, "_goal_pose_used_by_rewards", env._object_goal_poses_buf)
     out = [
         t["finger_reach_object_rate"].compute(T, ft0, ft1, ob0, ob1),
         t["finger_move_penalty"].compute(dt, ft0, ft1),

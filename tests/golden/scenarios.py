@@ -73,6 +73,11 @@ SCENARIOS = {
         config=_cfg(-1, 20, True, 1008, normalize_obs=False, apply_safety_damping=False,
                     reset_distribution={"object_initial_state": {"type": "default"},
                                         "robot_initial_state": {"type": "none"}})),
+    # moving goal (trifinger_env.py:1248-1253, :1267-1284): angular velocity sampled at goal resets, re-imposed on the
+    # goal body every step, goal pose read back from the simulator's goal rows (planted: random poses per step)
+    "moving_goal": dict(
+        N=24, T=7, seed=1010, reset_p=0.1, goal_reset_p=0.2, plant_goal_rows=True,
+        config=_cfg(4, 24, True, 1010, goal_movement={"rotation": {"activate": True, "rate_magnitude": 0.5}})),
     "d6_sym": dict(N=20, T=5, seed=1009, reset_p=0.25, goal_reset_p=0.25,
                    config=_cfg(6, 20, False, 1009, normalize_action=False,
                                reset_distribution={"object_initial_state": {"type": "none"}})),

@@ -51,6 +51,8 @@ class Golden:
         root = torch.zeros(T, N, 4, 13)
         root[..., 6] = 1.0
         root[:, :, 2] = torch.from_numpy(z["in/object_root"])
+        if "in/goal_root" in z.files:   # moving-goal scenarios: the goal body's rows as the simulator left them
+            root[:, :, 3] = torch.from_numpy(z["in/goal_root"])
         rb = torch.zeros(T, N, 20, 13)
         rb[:, :, list(FINGERTIP_BODIES)] = torch.from_numpy(z["in/fingertips"])
         return StateSequence(
@@ -87,7 +89,7 @@ def replay(env, g: Golden, check, inject: bool = True):
             check(t, "goal_reset_in", g.get(t, "goal_reset_in"))
             env.step(seq_action[t].clone())
         for key in ("reset_ids", "goal_reset_ids", "pre_sim_dof", "pre_sim_obj_root", "pre_sim_goal_root",
-                    "dof_index_list", "root_index_list0", "root_index_list1", "applied_torque",
+                    "dof_index_list", "root_index_list0", "root_index_list1", "root_index_list_move", "applied_torque",
                     "goal_pose", "goal_movement", "action_buf", "obs", "states", "reset_buf",
                     "goal_reset_buf", "steps_count", "successes", "terms", "reward", "sched_step"):
             if g.has(t, key):

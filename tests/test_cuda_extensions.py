@@ -104,3 +104,100 @@ def test_dr_noise_off_is_bit_identical_and_on_is_gaussian():
     # action noise: additive N(0, 0.03^2) before the clamp (|action| <= 0.5 here, so the clamp is inactive)
     ra = (on[0][2] - clean[0][2]).cpu().numpy().astype(np.float64)
     assert abs(ra.std() / 0.03 - 1) < 0.02 and stats.kstest(ra[:, 3] / 0.03, "norm").pvalue > 1e-3
+
+
+def test_goal_integrator_matches_its_oracle_and_rotates_at_the_imposed_rate():
+    """lg_integrate_goal (stand-in for PhysX on the moving goal body) against oracle/extensions.integrate_goal_rows;
+    properties: unit quaternions, rotation angle after K steps == |w| K dt, zero angular velocity is the identity."""
+    from leibnizgym_b200 import _native as nat
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.params import build_params
+    from oracle.extensions import integrate_goal_rows
+    N, dt, K = 4099, 0.02, 25
+    lib = nat.load()
+    from leibnizgym_b200.config import resolve_config
+    P = build_params(resolve_config(difficulty_config(4, N)), N)
+    g = torch.Generator().manual_seed(9)
+    root = torch.zeros(N, 4, 13)
+    root[..., 6] = 1.0
+    q = torch.randn(N, 4, generator=g)
+    root[:, 3, 3:7] = q / q.norm(dim=1, keepdim=True)
+    root[:, 3, 0:3] = torch.rand(N, 3, generator=g)
+    root[:, 3, 7:10] = 0.1 * torch.randn(N, 3, generator=g)
+    root[:, 3, 10:13] = 0.5 * torch.randn(N, 3, generator=g)
+    root[:7, 3, 10:13] = 0.0                               # w = 0: orientation must not move
+    root[7, 3, 10:13] = torch.tensor([0.0, 0.0, 3.0])
+    dev = root.cuda().contiguous()
+    S = nat.LgSimState(None, dev.data_ptr(), None, None, None)
+    q0 = dev[:, 3, 3:7].clone()
+    exp = root[:, 3].numpy().astype(np.float64)
+    for _ in range(K):
+        nat.check(lib.lg_integrate_goal(P, S, dt, torch.cuda.current_stream().cuda_stream), "lg_integrate_goal")
+        exp = integrate_goal_rows(exp, dt)
+    got = dev[:, 3].cpu().numpy().astype(np.float64)
+    assert np.abs(got - exp).max() < 5e-6, np.abs(got - exp).max()
+    assert torch.equal(dev[:, :3], root[:, :3].cuda())     # other actors untouched
+    assert np.abs(np.linalg.norm(got[:, 3:7], axis=1) - 1.0).max() < 1e-6
+    assert torch.equal(dev[:7, 3, 3:7], q0[:7])
+    ang = torch.zeros(N, device="cuda")
+    nat.check(lib.lg_quat_diff_rad(dev[:, 3, 3:7].contiguous().data_ptr(), q0.contiguous().data_ptr(), ang.data_ptr(), N,
+                                   torch.cuda.current_stream().cuda_stream), "lg_quat_diff_rad")
+    want = (root[:, 3, 10:13].norm(dim=1) * K * dt).numpy()
+    sel = want < 3.0                                        # below pi the geodesic angle is the integrated one
+    assert np.abs(ang.cpu().numpy()[sel] - want[sel]).max() < 2e-4
+
+
+def test_moving_goal_end_to_end_with_the_integrating_simulator():
+    """goal_movement.rotation on top of an integrating simulator: the goal pose buffer follows the goal body, which
+    turns at the sampled angular velocity; CUDA env == oracle env over the same (integrated) simulator state."""
+    from leibnizgym_b200.config import difficulty_config, resolve_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from oracle.extensions import integrate_goal_rows
+    from oracle.trifinger_oracle import OracleEnv, OracleSim
+    from tolerances import compare
+    N, T, dt = 1500, 6, 0.02
+    cfg = difficulty_config(4, N, seed=21, goal_movement={"rotation": {"activate": True, "rate_magnitude": 0.5}})
+    seq = make_sequence(77, T, N)
+
+    class IntegratingOracleSim(OracleSim):
+        def simulate(self):
+            keep = self.root.view(N, 4, 13)[:, 3].clone()
+            super().simulate()
+            rows = integrate_goal_rows(keep.numpy(), dt)
+            self.root.view(N, 4, 13)[:, 3] = torch.from_numpy(rows.astype(np.float32))
+
+    sim = SyntheticSim(seq.to("cuda:0"), "cuda:0")
+    env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=sim)
+    sim.enable_goal_integration(env._P, dt)
+    ora = OracleEnv(resolve_config(cfg), IntegratingOracleSim(seq, N))
+    g = torch.Generator().manual_seed(4)
+    d = (torch.rand(N, 24, generator=g).numpy(), torch.randn(N, 8, generator=g).numpy())
+    env.inject_draws(reset=d)
+    ora.inject_draws(reset=d)
+    env.reset()
+    ora.reset()
+    w = env._object_goal_movement_buf[:, 3:6].clone()
+    assert float(w.norm(dim=1).min()) > 0.0
+    q_start = env._object_goal_poses_buf[:, 3:7].clone()
+    for t in range(1, T):
+        env.step(seq.action[t].cuda())
+        ora.step(seq.action[t].clone())
+        for key, a, b in (("obs", env.obs_buf, ora.obs_buf), ("states", env.states_buf, ora.states_buf),
+                          ("goal_pose", env._object_goal_poses_buf, ora.goal_poses)):
+            ok, detail = compare(key, a.cpu().numpy(), b.numpy(), extra_atol=2e-6)
+            assert ok, (t, key, detail)
+        ok, detail = compare("reward", env.reward_buf.cpu().numpy(), ora.reward_buf.numpy(),
+                             extra_atol=1e-4 * np.abs(ora.reward_buf.numpy()).max())
+        assert ok, (t, detail)
+        # the goal pose the env holds IS the goal body's row, and the imposed angular velocity survives the step
+        assert torch.equal(env._object_goal_poses_buf, env._actors_root_state.view(N, 4, 13)[:, 3, 0:7])
+        assert torch.equal(env._actors_root_state.view(N, 4, 13)[:, 3, 10:13], w)
+    # reset() integrated the sampled pose once, each of the T-1 steps once more: total rotation |w| T dt
+    ang = torch.zeros(N, device="cuda")
+    from leibnizgym_b200 import _native as nat
+    nat.check(nat.load().lg_quat_diff_rad(env._object_goal_poses_buf[:, 3:7].contiguous().data_ptr(), q_start.data_ptr(),
+                                          ang.data_ptr(), N, torch.cuda.current_stream().cuda_stream), "lg_quat_diff_rad")
+    want = (w.norm(dim=1) * T * dt)
+    assert float((ang - want).abs().max()) < 2e-4

@@ -193,6 +193,62 @@ def test_vec_task_fused_clipping():
         vec.step(act[:, :8])
 
 
+def test_rl_games_adapter_contract():
+    """RlGamesGpuEnvAdapter (ref utils/rlg_train.py:89-154): persistent `full_state` dict with obs (+ states when
+    asymmetric), `[[], info]` in slot 3, spaces from the wrapper; values equal the oracle's clipped outputs."""
+    from leibnizgym_b200.config import difficulty_config, resolve_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from leibnizgym_b200.wrappers import RlGamesGpuEnvAdapter, VecTaskPython
+    from oracle.trifinger_oracle import OracleEnv, OracleSim
+    N, T = 777, 4
+    seq = make_sequence(5, T, N)
+    seq.dof_state[:, :, :, 1] *= 20.0            # |obs| > 5 after scaling: the clamp is exercised
+    g = torch.Generator().manual_seed(11)
+    d = (torch.rand(N, 24, generator=g).numpy(), torch.randn(N, 8, generator=g).numpy())
+    clip = lambda x: torch.clamp(x, -5.0, 5.0)   # noqa: E731
+    for asym in (True, False):
+        cfg = difficulty_config(2, N, asymmetric_obs=asym, seed=3)
+        made = []
+
+        def creator(**kw):
+            env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+            env.inject_draws(reset=d)
+            made.append(env)
+            return VecTaskPython(env, rl_device="cuda:0", clip_obs=5.0, clip_actions=1.0)
+
+        ad = RlGamesGpuEnvAdapter("rlgpu", N, env_creator=creator)     # resets once (ref :100)
+        env = made[-1]
+        ora = OracleEnv(resolve_config(cfg), OracleSim(seq, N))
+        ora.inject_draws(reset=d)
+        ora.reset()
+        info = ad.get_env_info()
+        assert info["num_envs"] == N and info["action_space"].shape == (9,) and info["observation_space"].shape == (41,)
+        assert ("state_space" in info) == asym and ad.get_number_of_agents() == 1
+        env.inject_draws(reset=d)
+        ora.inject_draws(reset=d)
+        first = ad.reset()
+        ora.reset()
+        assert (first is ad.full_state) if asym else torch.is_tensor(first)
+        _check("obs", first["obs"] if asym else first, clip(ora.obs_buf), ("reset", asym))
+        for t in range(1, T):
+            out, rew, done, extra = ad.step(seq.action[t].cuda())
+            ora.step(seq.action[t].clone())
+            w = ("adapter", asym, t)
+            assert isinstance(extra, list) and len(extra) == 2 and extra[0] == [] and isinstance(extra[1], dict)
+            assert (out is ad.full_state) if asym else torch.is_tensor(out)
+            _check("obs", out["obs"] if asym else out, clip(ora.obs_buf), w)
+            _check("reward", rew, ora.reward_buf, w)
+            assert torch.equal(done.cpu(), ora.reset_buf & ora.goal_reset_buf)      # SURVEY.md C1
+            if asym:
+                _check("states", out["states"], clip(ora.states_buf), w)
+                assert out["states"].data_ptr() == env._states_clipped.data_ptr()   # no copy on the way to the learner
+            assert "env/rewards/object_dist" in extra[1]
+    with pytest.raises(ValueError):
+        RlGamesGpuEnvAdapter("rlgpu", N)
+
+
 def test_own_random_stream_distributions():
     """The samplers on the kernel's Philox stream: r^2/R^2, theta, z uniform; goal quaternion uniform on S^3
     (components^2 ~ Beta(1/2, 3/2)); joint noise uniform; deterministic in (seed, epoch, env)."""

@@ -100,3 +100,36 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_rl_games_adapter_shapes_without_a_gpu():
+    """Adapter contract on a stub env (ref utils/rlg_train.py:89-154): dict vs tensor, persistent dict, [[], info]."""
+    import torch
+    from leibnizgym_b200.wrappers.rlg_adapter import RlGamesGpuEnvAdapter
+
+    class Stub:
+        def __init__(self, ns):
+            self.num_states, self.num_envs, self.calls = ns, 4, []
+            self.action_space, self.observation_space, self.state_space = "A", "O", "S"
+
+        def get_number_of_agents(self):
+            return 1
+
+        def reset(self):
+            self.calls.append("reset")
+            return torch.zeros(4, 3)
+
+        def get_state(self):
+            return torch.ones(4, self.num_states)
+
+        def step(self, a):
+            return torch.full((4, 3), 2.0), torch.zeros(4), torch.zeros(4, dtype=torch.bool), {"k": 1.0}
+
+    sym = RlGamesGpuEnvAdapter(env=Stub(0))
+    assert sym.env.calls == ["reset"] and not sym.use_global_obs and "state_space" not in sym.get_env_info()
+    out, r, d, extra = sym.step(torch.zeros(4, 9))
+    assert torch.is_tensor(out) and extra == [[], {"k": 1.0}] and torch.is_tensor(sym.reset())
+    asym = RlGamesGpuEnvAdapter(env=Stub(5))
+    out, r, d, extra = asym.step(torch.zeros(4, 9))
+    assert out is asym.full_state and set(out) == {"obs", "states"} and out["states"].shape == (4, 5)
+    assert asym.reset() is asym.full_state and asym.get_env_info()["state_space"] == "S"

@@ -11,7 +11,7 @@ import numpy as np
 RTOL = 1e-5
 
 EXACT = {"reset_in", "goal_reset_in", "reset_ids", "goal_reset_ids", "dof_index_list", "root_index_list0",
-         "root_index_list1", "reset_buf", "goal_reset_buf", "steps_count", "successes", "sched_step"}
+         "root_index_list1", "root_index_list_move", "reset_buf", "goal_reset_buf", "steps_count", "successes", "sched_step"}
 
 # absolute floors
 ATOL = {
