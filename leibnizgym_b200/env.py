@@ -473,6 +473,25 @@ class TrifingerEnv(IsaacEnvBase):
         self._step_info = self._make_info()
         return self._obs_buf, self._reward_buf, self._dones, self._step_info
 
+    # -- checkpoint / resume (the reference only dumps its config, env_base.py:295-309) ------
+    def state_dict(self) -> dict:
+        from .checkpoint import env_state_dict
+        return env_state_dict(self)
+
+    def load_state_dict(self, state: dict) -> None:
+        from .checkpoint import load_env_state_dict
+        load_env_state_dict(self, state)
+
+    def save_checkpoint(self, path: str) -> str:
+        """Everything the MDP carries between steps (and SyntheticSim's tensors) into one .npz; returns the path."""
+        from .checkpoint import save_env_state
+        return save_env_state(self, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        """Continue bit-identically from `save_checkpoint` (same config, shard geometry and simulator sequence)."""
+        from .checkpoint import load_env_state
+        load_env_state(self, path)
+
     def _make_info(self) -> Dict[str, torch.Tensor]:
         """`_step_info` of the reference (trifinger_env.py:554, :1068, :1076, :1099) as 0-d fp64 views
         of the per-step statistics buffer: valid until the next step overwrites them; values are

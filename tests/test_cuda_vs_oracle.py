@@ -342,3 +342,56 @@ def test_host_pipeline_equals_plain_step(chunks, asym):
         for k in i1:
             assert abs(float(i1[k]) - float(i2[k])) <= 1e-9 * max(1.0, abs(float(i1[k]))), k
     assert int(env_a._steps_count_buf.max()) <= 2 and o2.device.type == "cpu" and o2.is_pinned()
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """save_checkpoint after step k, load into a fresh env: steps k+1.. equal the uninterrupted run bit for bit —
+    goal poses, counters, history, the kernel's own Philox epoch, the schedule clock."""
+    import copy
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from leibnizgym_b200.wrappers import VecTaskPython
+    N, T = 3000, 12
+    cfg = difficulty_config(4, N, seed=9, episode_length=3,
+                            reset_distribution={"robot_initial_state": {"type": "random", "dof_pos_stddev": 0.4,
+                                                                        "dof_vel_stddev": 0.2}},
+                            termination_conditions={"success": {"activate": True, "bonus": 5000.0,
+                                                                "position_tolerance": 0.2, "orientation_tolerance": 3.0}},
+                            goal_movement={"rotation": {"activate": True, "rate_magnitude": 0.5}})
+    seq = make_sequence(13, T, N)
+
+    def build():
+        env = TrifingerEnv(copy.deepcopy(cfg), device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+        return env, VecTaskPython(env, rl_device="cuda:0")
+
+    def snap(env, vec, out):
+        return [x.clone() for x in (out[0], out[1], out[2], vec.get_state(), env._object_goal_poses_buf, env._steps_count_buf,
+                                    env._reset_buf, env._goal_reset_buf, env._successes, env.reset_env_ids,
+                                    env._dof_state, env._actors_root_state, env._step_stats)]
+
+    env_a, vec_a = build()
+    vec_a.reset()
+    for t in range(1, 6):
+        vec_a.step(seq.action[t].cuda())
+    path = env_a.save_checkpoint(str(tmp_path / "ckpt" / "env_state"))
+    assert path.endswith(".npz")
+    want = [snap(env_a, vec_a, vec_a.step(seq.action[t].cuda())) for t in range(6, T)]
+    assert int(sum(w[9].numel() for w in want)) > 0            # resets (own random stream) happened after the checkpoint
+
+    env_b, vec_b = build()                                      # fresh process state: never reset, clock at zero
+    env_b.load_checkpoint(path)
+    assert env_b.env_steps_count == 6 * N                       # reset() + 5 steps
+    got = [snap(env_b, vec_b, vec_b.step(seq.action[t].cuda())) for t in range(6, T)]
+    for t, (g, w) in enumerate(zip(got, want)):
+        for i, (a, b) in enumerate(zip(g, w)):
+            if i == len(g) - 1:   # the fp64 statistics are atomic sums over CTAs: order-dependent in the last bits
+                assert torch.allclose(a, b, rtol=1e-12, atol=0.0), (t, i)
+            else:
+                assert torch.equal(a, b), (t, i)
+
+    other = TrifingerEnv(difficulty_config(4, N + 1, seed=9), device="cuda:0", verbose=False,
+                         sim=SyntheticSim(make_sequence(13, 2, N + 1).to("cuda:0"), "cuda:0"))
+    with pytest.raises(ValueError):
+        other.load_checkpoint(path)
