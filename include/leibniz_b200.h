@@ -208,6 +208,10 @@ typedef struct LgBuffers {
   const float* inject_reset_n;  /* [k, 8]  goal quaternion 0:4 | ang-vel axis 4:7 | magnitude 7  */
   const float* inject_goal_u;   /* same layouts for the goal-reset list                          */
   const float* inject_goal_n;
+  /* optional bfloat16 copies of the outputs for the policy / value networks: round-to-nearest-even
+     of the clipped values when obs_clipped / states_clipped are requested, else of obs / states */
+  uint16_t* obs_bf16;       /* [N, obs_dim]   */
+  uint16_t* states_bf16;    /* [N, state_dim] */
 } LgBuffers;
 
 int lg_version(void);

@@ -7,6 +7,7 @@
 //   post_physics_kernel  obs/states fill + scale_transform, six reward terms, termination,
 //                        step counters / timeouts / dones, episode statistics; one lane per output column
 // Reference paths are relative to /root/reference/leibnizgym/.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -100,6 +101,9 @@ __device__ __forceinline__ float div_by_const(float num, float span, float rcp, 
 }
 constexpr float kDivSafeMax = 1.2676506e30f;  // 2^100
 
+// bfloat16 bits of a float, round-to-nearest-even (what torch's .to(torch.bfloat16) does)
+__device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+
 // Cold path: re-emit one lane's output column with IEEE division (only when a numerator left the fast
 // division's window).  Re-reads the source so the hot path keeps its registers.
 template <int STATE, int OBS, bool ASYM>
@@ -115,6 +119,8 @@ __device__ __noinline__ void output_exact(const LgParams& P, const LgBuffers& B,
     if (dcol < OBS) B.obs[e * OBS + dcol] = v;
     if (ASYM && B.states_clipped) B.states_clipped[e * STATE + dcol] = vc;
     if (dcol < OBS && B.obs_clipped) B.obs_clipped[e * OBS + dcol] = vc;
+    if (ASYM && B.states_bf16) B.states_bf16[e * STATE + dcol] = to_bf16(B.states_clipped ? vc : v);
+    if (dcol < OBS && B.obs_bf16) B.obs_bf16[e * OBS + dcol] = to_bf16(B.obs_clipped ? vc : v);
   }
 }
 
@@ -309,13 +315,19 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     // actor observation, before scale_transform; the critic's states stay clean.  sigma = 0 -> skipped.
     const float sigma = (EXT && P.dr_activate && to_obs) ? __ldg(B.scale_table + 3 * LG_MAX_STATE_DIM + dcol) : 0.0f;
     const bool noisy = EXT && __any_sync(0xffffffffu, sigma != 0.0f);
+    // optional bf16 copies for the policy / value networks: of the clipped values when the
+    // wrapper's clamp is fused in, else of the scaled values
+    uint16_t* stb = (EXT && ASYM && B.states_bf16) ? B.states_bf16 + e0 * L::STATE + st_off : nullptr;
+    uint16_t* obb = (EXT && B.obs_bf16) ? B.obs_bf16 + e0 * L::OBS + ob_off : nullptr;
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
       const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
       if (FULLC || k < cnt) {
         if (ASYM) {
           st[k * L::STATE] = sv;
-          if (CLIP) stc[k * L::STATE] = fminf(fmaxf(sv, -clip), clip);
+          const float svc = CLIP ? fminf(fmaxf(sv, -clip), clip) : sv;
+          if (CLIP) stc[k * L::STATE] = svc;
+          if (EXT && stb) stb[k * L::STATE] = to_bf16(svc);
         }
         if (to_obs) {
           float ov = sv;
@@ -329,7 +341,9 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
             ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
           }
           ob[k * L::OBS] = ov;
-          if (CLIP) obc[k * L::OBS] = fminf(fmaxf(ov, -clip), clip);
+          const float ovc = CLIP ? fminf(fmaxf(ov, -clip), clip) : ov;
+          if (CLIP) obc[k * L::OBS] = ovc;
+          if (EXT && obb) obb[k * L::OBS] = to_bf16(ovc);
         }
       }
     }
@@ -1090,8 +1104,8 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
   const int E = P->action_dim == 9 ? pick_tile_envs(P->num_envs) : 32;
   const unsigned grid = (unsigned)((P->num_envs + E - 1) / E);
   cudaError_t err;
-  // rarely-used paths (DR noise, keypoint term, moving goal) live in their own instantiation: switched off they cost nothing
-  const bool ext = P->dr_activate || P->goal_rotation || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1);
+  // rarely-used paths (DR noise, keypoint term, moving goal, bf16 copies) live in their own instantiation: switched off they cost nothing
+  const bool ext = P->dr_activate || P->goal_rotation || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1) || B->obs_bf16 || B->states_bf16;
 #define LG_K(AD, AS, CL, EE) (ext ? launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, true>, grid, lg::kPostThreads, st, *P, *S, *B, cf) \
                                   : launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, false>, grid, lg::kPostThreads, st, *P, *S, *B, cf))
 #define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))

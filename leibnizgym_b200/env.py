@@ -290,6 +290,7 @@ class TrifingerEnv(IsaacEnvBase):
         self._applied_torque = torch.zeros((N, 9), device=dev, dtype=torch.float)
         self._term_rewards = None
         self._obs_clipped = self._states_clipped = None
+        self._obs_bf16 = self._states_bf16 = None
         self._step_stats = torch.zeros(nat.LG_NUM_STATS, device=dev, dtype=torch.float64)
         self._reset_ids = torch.zeros(N, device=dev, dtype=torch.long)
         self._goal_reset_ids = torch.zeros(N, device=dev, dtype=torch.long)
@@ -343,6 +344,7 @@ class TrifingerEnv(IsaacEnvBase):
         b.goal_pose, b.goal_movement, b.history = p(self._object_goal_poses_buf), p(self._object_goal_movement_buf), p(self._history)
         b.applied_torque, b.term_rewards = p(self._applied_torque), p(self._term_rewards)
         b.step_stats = p(self._step_stats)
+        b.obs_bf16, b.states_bf16 = p(self._obs_bf16), p(self._states_bf16)
         b.reset_ids, b.goal_reset_ids, b.counts = p(self._reset_ids), p(self._goal_reset_ids), p(self._counts)
         b.robot_indices, b.reset_root_indices, b.goal_root_indices = p(self._robot_indices), p(self._reset_root_indices), p(self._goal_root_indices)
         b.scan_status, b.control = p(self._scan_status), p(self._control)
@@ -378,6 +380,16 @@ class TrifingerEnv(IsaacEnvBase):
         if clip_actions is not None:
             self._P.clip_actions, self._P.clip_input_actions = float(clip_actions), 1
         self._bind()
+
+    def enable_bf16_outputs(self):
+        """Also emit bfloat16 copies of the (clipped, when enabled) observations and states from the same pass, for
+        policy / value networks that run in bf16: round-to-nearest-even, i.e. bit-identical to
+        `.to(torch.bfloat16)` of the fp32 outputs, without the extra read-convert-write pass."""
+        self._obs_bf16 = torch.zeros(self._obs_buf.shape, device=self._torch_device, dtype=torch.bfloat16)
+        self._states_bf16 = (torch.zeros(self._states_buf.shape, device=self._torch_device, dtype=torch.bfloat16)
+                             if self.config["asymmetric_obs"] else None)
+        self._bind()
+        return self._obs_bf16, self._states_bf16
 
     def enable_host_outputs(self, clip_obs: Optional[float] = None, clip_actions: Optional[float] = None):
         """Zero-copy result path for a HOST-side learner or simulator: the fused kernels store what the

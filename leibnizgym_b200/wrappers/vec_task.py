@@ -95,11 +95,17 @@ class VecTask:
 
 class VecTaskPython(VecTask):
     def __init__(self, task: IsaacEnvBase, rl_device: str, clip_obs: float = 5.0, clip_actions: float = 1.0,
-                 host_pipeline_chunks: int = 0):
+                 host_pipeline_chunks: int = 0, obs_dtype: torch.dtype = torch.float32):
         """`host_pipeline_chunks` > 0 (host-resident simulator and learner, rl_device 'cpu'): step through
-        host_pipeline.HostPipeline, which overlaps the state upload, the kernels and the result download."""
+        host_pipeline.HostPipeline, which overlaps the state upload, the kernels and the result download.
+        `obs_dtype=torch.bfloat16`: hand the learner bf16 observations / states, emitted by the fused pass itself."""
         super().__init__(task, rl_device, clip_obs, clip_actions)
         self._pipeline = None
+        if obs_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("obs_dtype must be torch.float32 or torch.bfloat16")
+        self._bf16 = obs_dtype == torch.bfloat16
+        if self._bf16 and (host_pipeline_chunks > 0 or not hasattr(task, "enable_bf16_outputs")):
+            raise ValueError("bf16 outputs need the fused device path")
         self._fused = hasattr(task, "enable_clipped_outputs")
         if self._fused:
             if host_pipeline_chunks > 0:
@@ -111,17 +117,21 @@ class VecTaskPython(VecTask):
                 task.enable_host_outputs(self._clip_obs, self._clip_actions)
             else:
                 task.enable_clipped_outputs(self._clip_obs, self._clip_actions)
+            if self._bf16:
+                task.enable_bf16_outputs()
 
     def get_state(self) -> torch.Tensor:
         if self._pipeline is not None:
             return self._pipeline.h_states
+        if self._bf16:
+            return self._task._states_bf16.to(self._rl_device)
         if self._fused and self._task._states_clipped is not None:
             return self._task._states_clipped.to(self._rl_device)
         return torch.clamp(self._task.states_buf, -self._clip_obs, self._clip_obs).to(self._rl_device)
 
     def reset(self) -> torch.Tensor:
-        obs = self._task.reset()
-        return torch.clamp(obs, -self._clip_obs, self._clip_obs).to(self._rl_device)
+        obs = torch.clamp(self._task.reset(), -self._clip_obs, self._clip_obs)
+        return (obs.to(torch.bfloat16) if self._bf16 else obs).to(self._rl_device)
 
     def step(self, actions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         if self._task.visualize:
@@ -131,7 +141,7 @@ class VecTaskPython(VecTask):
         if self._fused:
             # action clamp, obs clamp and states clamp all happen inside the two fused launches
             _, rew, is_done, info = self._task.step(actions)
-            obs = self._task._obs_clipped
+            obs = self._task._obs_bf16 if self._bf16 else self._task._obs_clipped
         else:
             obs, rew, is_done, info = self._task.step(torch.clamp(actions, -self._clip_actions, self._clip_actions))
             obs = torch.clamp(obs, -self._clip_obs, self._clip_obs)

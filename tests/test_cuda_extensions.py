@@ -201,3 +201,40 @@ def test_moving_goal_end_to_end_with_the_integrating_simulator():
                                           ang.data_ptr(), N, torch.cuda.current_stream().cuda_stream), "lg_quat_diff_rad")
     want = (w.norm(dim=1) * T * dt)
     assert float((ang - want).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("asym", [True, False])
+def test_bf16_outputs_are_the_rounded_fp32_outputs(asym):
+    """Optional bf16 emission: bit-identical to `.to(torch.bfloat16)` of the clipped fp32 outputs,
+    through the wrapper; the fp32 outputs themselves do not change when it is switched on."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    from leibnizgym_b200.wrappers import VecTaskPython
+    N, T = 2077, 4
+    seq = make_sequence(3, T, N)
+    seq.dof_state[:, :, :, 1] *= 20.0   # some values beyond the clamp
+    cfg = difficulty_config(3, N, asymmetric_obs=asym, seed=8)
+
+    def build(dtype):
+        env = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+        return env, VecTaskPython(env, rl_device="cuda:0", obs_dtype=dtype)
+
+    env_f, vec_f = build(torch.float32)
+    env_b, vec_b = build(torch.bfloat16)
+    o_f, o_b = vec_f.reset(), vec_b.reset()
+    assert o_b.dtype == torch.bfloat16 and torch.equal(o_b, o_f.to(torch.bfloat16))
+    for t in range(1, T):
+        of, rf, df, _ = vec_f.step(seq.action[t].cuda())
+        ob, rb, db, _ = vec_b.step(seq.action[t].cuda())
+        assert ob.dtype == torch.bfloat16 and ob.shape == of.shape
+        assert torch.equal(ob, of.to(torch.bfloat16)) and torch.equal(rf, rb) and torch.equal(df, db)
+        assert torch.equal(env_f.obs_buf, env_b.obs_buf) and torch.equal(env_f._obs_clipped, env_b._obs_clipped)
+        if asym:
+            sb = vec_b.get_state()
+            assert sb.dtype == torch.bfloat16 and torch.equal(sb, vec_f.get_state().to(torch.bfloat16))
+            assert torch.equal(env_f.states_buf, env_b.states_buf)
+    assert float(of.abs().max()) == 5.0
+    with pytest.raises(ValueError):
+        VecTaskPython(env_f, rl_device="cuda:0", obs_dtype=torch.float16)
