@@ -47,8 +47,17 @@ FALLBACK_HBM_GBS = 6650.0
 WORKLOADS = {
     "c2": dict(desc="trifinger_difficulty_2, asymmetric obs+states, 16384 envs/GPU", difficulty=2, envs=16384,
                asym=True, seed=1002, reset_p=0.0),
-    "c3": dict(desc="trifinger_difficulty_3, asymmetric, 65536 envs/GPU, 5% forced resets/step", difficulty=3,
-               envs=65536, asym=True, seed=1003, reset_p=0.05),
+    # DR noise (extension, no reference code) + goal resampling forced on 5 % of the envs per step
+    "c3": dict(desc="trifinger_difficulty_3, asymmetric, 65536 envs/GPU, DR obs/action noise (extension), goal "
+                    "resampling forced on 5% of envs/step", difficulty=3, envs=65536, asym=True, seed=1003, reset_p=0.0,
+               goal_p=0.05, dr=True),
+    "c3ref": dict(desc="trifinger_difficulty_3, asymmetric, 65536 envs/GPU, goal resampling forced on 5% of envs/step "
+                       "(reference features only)", difficulty=3, envs=65536, asym=True, seed=1003, reset_p=0.0, goal_p=0.05),
+    "c3reset": dict(desc="trifinger_difficulty_3, asymmetric, 65536 envs/GPU, 5% forced resets/step", difficulty=3,
+                    envs=65536, asym=True, seed=1003, reset_p=0.05),
+    # the keypoint pose reward is an extension term, reported separately from the headline
+    "c2kp": dict(desc="trifinger_difficulty_2 + keypoint pose reward (extension), asymmetric, 16384 envs/GPU", difficulty=2,
+                 envs=16384, asym=True, seed=1002, reset_p=0.0, keypoint=True),
     "c4": dict(desc="trifinger_difficulty_4, asymmetric obs+states, 32768 envs/GPU (262144 over 8)", difficulty=4,
                envs=32768, asym=True, seed=1004, reset_p=0.0),
     "c5": dict(desc="reset-heavy: difficulty 4, asymmetric, 16384 envs/GPU, 30% envs reset per step", difficulty=4,
@@ -56,6 +65,22 @@ WORKLOADS = {
     "c2sym": dict(desc="trifinger_difficulty_2, symmetric obs only, 16384 envs/GPU", difficulty=2, envs=16384,
                   asym=False, seed=1002, reset_p=0.0),
 }
+
+
+
+def workload_config(wl, num_envs, extensions=True):
+    """Env config of a workload; `extensions=False` drops what the reference does not implement (CPU legs)."""
+    over = {}
+    if extensions and wl.get("dr"):
+        over["domain_randomization"] = {"activate": True, "action_noise_std": 0.02,
+                                        "obs_noise_std": {"robot_q": 0.005, "robot_u": 0.05, "object_q": 0.002,
+                                                          "object_q_des": 0.0, "command": 0.0}}
+    cfg = difficulty_config(wl["difficulty"], num_envs, asymmetric_obs=wl["asym"], seed=wl["seed"], **over)
+    if extensions and wl.get("keypoint"):
+        from leibnizgym_b200.config import KEYPOINT_TERM_DEFAULT
+        cfg["reward_terms"]["keypoint"] = dict(KEYPOINT_TERM_DEFAULT, activate=True)
+    return cfg
+
 
 # algorithmic bytes per env-step (SURVEY.md §8d; derivation in DESIGN.md §5)
 POST_BYTES = {True: 526 + 695, False: 298 + 243}
@@ -168,10 +193,11 @@ def time_cpu_path(wl: dict, envs: int, steps: int, warmup: int, max_seconds: flo
 
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     torch.set_num_threads(int(os.environ.get("LG_CPU_THREADS", os.cpu_count() or 1)))
-    cfg = resolve_config(difficulty_config(wl["difficulty"], envs, asymmetric_obs=wl["asym"], seed=wl["seed"]))
+    cfg = resolve_config(workload_config(wl, envs, extensions=False))   # the reference has no DR noise / keypoint term
     T = 4
     seq = make_sequence(wl["seed"], T, envs)
     masks = bernoulli_masks(wl["seed"], T, envs, wl["reset_p"])
+    gmasks = bernoulli_masks(wl["seed"] + 7, T, envs, wl.get("goal_p", 0.0))
     env = OracleEnv(cfg, TimedSim(seq, envs))
     env.reset()
     for t in range(warmup):
@@ -182,6 +208,8 @@ def time_cpu_path(wl: dict, envs: int, steps: int, warmup: int, max_seconds: flo
     while done < steps:
         if masks is not None:
             env.reset_buf |= masks[done % T]
+        if gmasks is not None:
+            env.goal_reset_buf |= gmasks[done % T]
         env.step(seq.action[done % T])
         done += 1
         if time.perf_counter() - t0 > max_seconds:
@@ -246,12 +274,13 @@ def run_gpu(args, wl):
     R = args.ring
     asym = wl["asym"]
 
-    cfg = difficulty_config(wl["difficulty"], N * world, asymmetric_obs=asym, seed=wl["seed"])
+    cfg = workload_config(wl, N * world)
     ring = make_sequence(wl["seed"], R, N, device=dev, first_env=rank * N)
     masks = bernoulli_masks(wl["seed"] + rank, R, N, wl["reset_p"], device=dev)
+    gmasks = bernoulli_masks(wl["seed"] + 7 + rank, R, N, wl.get("goal_p", 0.0), device=dev)
     env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(ring, dev), rank=rank, world_size=world)
     env.reset()
-    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks)
+    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks, inject_goal_masks=gmasks)
 
     stream = torch.cuda.Stream()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -323,7 +352,9 @@ def run_gpu(args, wl):
         "config": {"workload": wl["desc"], "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"dp{world}",
                    "l2_policy": f"inputs larger than L2: ring of {R} distinct simulator states "
                                 f"({ring.nbytes() / 2**20:.0f} MiB) and {R} output slots per GPU",
-                   "steps_per_graph": C, "reset_fraction_per_step": wl["reset_p"]},
+                   "steps_per_graph": C, "reset_fraction_per_step": wl["reset_p"],
+                   "goal_reset_fraction_per_step": wl.get("goal_p", 0.0),
+                   "extensions": [k for k in ("dr", "keypoint") if wl.get(k)]},
         "roofline": {"bound": "hbm", "kernel": "post_physics_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N, asym), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,

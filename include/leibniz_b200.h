@@ -212,6 +212,10 @@ typedef struct LgBuffers {
      of the clipped values when obs_clipped / states_clipped are requested, else of obs / states */
   uint16_t* obs_bf16;       /* [N, obs_dim]   */
   uint16_t* states_bf16;    /* [N, state_dim] */
+  /* optional [N] bool masks OR-ed into _reset_buf / _goal_reset_buf by lg_pre_physics before the compaction: what a
+     caller does with `env._reset_buf |= mask` between steps (tests, reset-heavy workloads), without a separate pass */
+  const uint8_t* force_reset;
+  const uint8_t* force_goal_reset;
 } LgBuffers;
 
 int lg_version(void);

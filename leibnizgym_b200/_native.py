@@ -83,7 +83,8 @@ class LgBuffers(C.Structure):
         "successes", "dones", "steps_count", "goal_pose", "goal_movement", "history", "applied_torque",
         "term_rewards", "step_stats", "reset_ids", "goal_reset_ids", "counts",
         "robot_indices", "reset_root_indices", "goal_root_indices", "scan_status", "control", "reward_coef", "scale_table",
-        "inject_reset_u", "inject_reset_n", "inject_goal_u", "inject_goal_n", "obs_bf16", "states_bf16")]
+        "inject_reset_u", "inject_reset_n", "inject_goal_u", "inject_goal_n", "obs_bf16", "states_bf16",
+        "force_reset", "force_goal_reset")]
 
 
 class LgHostStep(C.Structure):

@@ -298,48 +298,54 @@ __device__ __forceinline__ void apply_goal_sample(const LgParams& P, const LgSim
   for (int c = 0; c < 3; ++c) { gm[3 + c] = angvel[c]; row[7 + c] = gm[c]; row[10 + c] = angvel[c]; }
 }
 
-// _reset_impl for ONE env (trifinger_env.py:373-411, :1101-1192); index lists are written by the caller.
-__device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                              int64_t e, const DrawSource& dr) {
-  // A) episode bookkeeping (:382-387)
-  B.reset[e] = 0;
-  B.steps_count[e] = 0;
-  B.successes[e] = 0;
-  float* act = B.action + e * P.action_dim;
-  for (int c = 0; c < P.action_dim; ++c) act[c] = 0.0f;
-  // B) robot joint state (:1119-1144); the zeroing of fingertip history entry 1 (:1146-1147)
-  //    is a dead write in the reference and has no counterpart here
-  if (P.robot_reset != LG_RESET_NONE) {
+// _reset_impl for ONE env (trifinger_env.py:373-411, :1101-1192) cut into EIGHT independent sub-tasks, so that the
+// fused kernel can run them on different warps (uniform control flow inside a warp) instead of one long serial
+// chain per resetting env.  The draws are counter-based (or injected by column), so every sub-task fetches exactly
+// the columns it needs; the arithmetic per output is unchanged.  Index lists are written by the caller.
+//   0..4  robot joint state, uniform block b = canonical columns 4b..4b+3 (pos 0..8 | vel 9..17)     :1119-1144
+//   5     object pose -> root row + history entry                                                      :1164-1192
+//   6     goal pose / movement (skipped when a goal reset of the same env follows and overwrites it)   :408-411
+//   7     episode bookkeeping                                                                           :382-387
+// The zeroing of fingertip history entry 1 (:1146-1147) is a dead write in the reference and has
+// no counterpart here.
+constexpr int kResetSubtasks = 8;
+// `dof_mirror`: optional second destination of the env's new joint-state row (the fused kernel's shared-memory copy,
+// from which the torque is computed right afterwards).
+__device__ __forceinline__ void reset_subtask(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
+                                              int sub, const DrawSource& dr, bool goal_reset_follows,
+                                              float* dof_mirror = nullptr) {
+  if (sub < 5) {
+    if (P.robot_reset == LG_RESET_NONE) return;
     float* dof = S.dof_state + e * 18;
-    float un[20];
-    if (P.robot_reset == LG_RESET_RANDOM) {
+    float un[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const bool random = P.robot_reset == LG_RESET_RANDOM;
+    if (random) dr.uniform4(sub, un);
 #pragma unroll
-      for (int b = 0; b < 5; ++b) dr.uniform4(b, un + 4 * b);   // columns 0..17: one Philox block per 4
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      float pos = P.dof_default_pos[j], vel = P.dof_default_vel[j];
-      if (P.robot_reset == LG_RESET_RANDOM) {
-        const float np_ = 2.0f * un[j] - 1.0f;
-        const float nv_ = 2.0f * un[9 + j] - 1.0f;
-        pos = pos + (float)P.dof_pos_stddev * np_;
-        vel = vel + (float)P.dof_vel_stddev * nv_;
+    for (int q = 0; q < 4; ++q) {
+      const int i = 4 * sub + q;            // canonical column: joint position i (< 9) or velocity i - 9
+      if (i < 18) {
+        const bool is_vel = i >= 9;
+        const int j = is_vel ? i - 9 : i;
+        float x = is_vel ? P.dof_default_vel[j] : P.dof_default_pos[j];
+        if (random) {
+          const float n = 2.0f * un[q] - 1.0f;
+          x = x + (float)(is_vel ? P.dof_vel_stddev : P.dof_pos_stddev) * n;
+        }
+        dof[2 * j + (is_vel ? 1 : 0)] = x;
+        if (dof_mirror) dof_mirror[2 * j + (is_vel ? 1 : 0)] = x;
       }
-      dof[2 * j] = pos;
-      dof[2 * j + 1] = vel;
     }
-  }
-  // C) object pose (:1164-1192): history entry 0 gets (pose, 0 velocity); its pose part is what
-  //    the next post-physics pass reads as "previous object pose" 
-  float ub5[4];
-  dr.uniform4(5, ub5);                           // column 20 (object yaw) and the goal columns 21..23
-  if (P.object_reset != LG_RESET_NONE) {
+  } else if (sub == 5) {
+    // history entry 0 gets (pose, 0 velocity); its pose part is what the next post-physics pass reads as
+    // "previous object pose" 
+    if (P.object_reset == LG_RESET_NONE) return;
     float x = 0.0f, y = 0.0f;
     const float z = (float)P.cube_half_size;
     Quat q{0.0f, 0.0f, 0.0f, 1.0f};
     if (P.object_reset == LG_RESET_RANDOM) {
-      float ub4[4];
+      float ub4[4], ub5[4];
       dr.uniform4(4, ub4);                       // columns 18, 19 (disc radius, angle) are lanes 2, 3
+      dr.uniform4(5, ub5);                       // column 20 (object yaw)
       sample_disc(ub4[2], ub4[3], (float)P.max_com_distance, x, y);
       q = sample_yaw(ub5[0]);
     }
@@ -350,9 +356,22 @@ __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimStat
     for (int c = 0; c < 7; ++c) { h[c] = pose[c]; row[c] = pose[c]; }
 #pragma unroll
     for (int c = 7; c < 13; ++c) row[c] = 0.0f;
+  } else if (sub == 6) {
+    if (!goal_reset_follows) apply_goal_sample(P, S, B, e, dr);   // goal columns 21..23 live in uniform block 5
+  } else {
+    B.reset[e] = 0;
+    B.steps_count[e] = 0;
+    B.successes[e] = 0;
+    float* act = B.action + e * P.action_dim;
+    for (int c = 0; c < P.action_dim; ++c) act[c] = 0.0f;
   }
-  // D) goal (:408-411)
-  apply_goal_sample(P, S, B, e, dr, ub5);
+}
+
+// all of it for one env, in the reference's order (hooks on explicit id lists)
+__device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimState& S, const LgBuffers& B,
+                                              int64_t e, const DrawSource& dr) {
+  reset_subtask(P, S, B, e, 7, dr, false);
+  for (int sub = 0; sub < 7; ++sub) reset_subtask(P, S, B, e, sub, dr, false);
 }
 
 // _pre_step for ONE env (trifinger_env.py:442-498): action -> applied joint torque

@@ -165,7 +165,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   __shared__ float s_tips[E * 9];       // fingertip positions
   __shared__ float s_hist[E * HS];      // previous fingertip positions (9) + previous object pose (7)
   __shared__ float s_coef[C_COUNT];
-  __shared__ float s_part[9][E];        // sub-task results of the reward warps
+  __shared__ float s_part[12][E];       // sub-task results of the reward warps
   __shared__ float s_stat[LG_NUM_STATS][E + 1];
 
   const int tid = threadIdx.x;
@@ -319,6 +319,8 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     // wrapper's clamp is fused in, else of the scaled values
     uint16_t* stb = (EXT && ASYM && B.states_bf16) ? B.states_bf16 + e0 * L::STATE + st_off : nullptr;
     uint16_t* obb = (EXT && B.obs_bf16) ? B.obs_bf16 + e0 * L::OBS + ob_off : nullptr;
+    uint64_t noise_group = ~0ull;     // envs come in groups of 4 (by GLOBAL index): one Philox block -> 4 normals
+    float nz0 = 0.0f, nz1 = 0.0f, nz2 = 0.0f, nz3 = 0.0f;
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
       const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
@@ -332,12 +334,17 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
         if (to_obs) {
           float ov = sv;
           if (noisy) {
-            const uint64_t genv = (uint64_t)(P.env_offset + e0 + env_first + k);
-            const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, (uint32_t)dcol,
-                                          __float_as_uint(s_coef[C_NOISE_EPOCH])},
-                                       (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-            float n0, n1;
-            box_muller(r.x, r.y, n0, n1);
+            const uint64_t genv = (uint64_t)(P.env_offset + e0 + env_first + k), grp = genv >> 2;
+            if (grp != noise_group) {
+              noise_group = grp;
+              const U4 r = philox4x32_10(U4{(uint32_t)grp, (uint32_t)(grp >> 32) ^ kPurposeNoise, (uint32_t)dcol,
+                                            __float_as_uint(s_coef[C_NOISE_EPOCH])},
+                                         (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+              box_muller(r.x, r.y, nz0, nz1);
+              box_muller(r.z, r.w, nz2, nz3);
+            }
+            const int which = (int)(genv & 3);
+            const float n0 = which == 0 ? nz0 : which == 1 ? nz1 : which == 2 ? nz2 : nz3;
             ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
           }
           ob[k * L::OBS] = ov;
@@ -419,24 +426,27 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
           // previous-orientation angle for object_rot_delta (rewards.py:179)
           const Quat pq{hist[12], hist[13], hist[14], hist[15]};
           s_part[7][env] = fabsf(quat_diff_rad(pq, gq));
-          // extension (no reference code): keypoint pose reward
-          //   w dt mean_k lgsk(|kp_k - kp_k^goal|; scale, eps), kp_k = p + R(q) c_k over the 8 cube corners
-          if (EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1)) {
-            const Quat oq{obj[3], obj[4], obj[5], obj[6]};
-            const float h = (float)P.cube_half_size;
-            float acc = 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const float cx = (kk & 1) ? h : -h, cy = (kk & 2) ? h : -h, cz = (kk & 4) ? h : -h;
-              float ax, ay, az, bx, by, bz;
-              quat_rotate(oq, cx, cy, cz, ax, ay, az);
-              quat_rotate(gq, cx, cy, cz, bx, by, bz);
-              const float dd = norm3((obj[0] + ax) - (gx + bx), (obj[1] + ay) - (gy + by), (obj[2] + az) - (gz + bz));
-              acc = acc + lgsk(dd, s_coef[C_KP_SCALE], s_coef[C_KP_EPS]);
-            }
-            s_part[8][env] = s_coef[C_KP_W] * (acc * 0.125f);
-          }
         }
+      }
+      // extension (no reference code): keypoint pose reward
+      //   w dt mean_k lgsk(|kp_k - kp_k^goal|; scale, eps), kp_k = p + R(q) c_k over the 8 cube corners;
+      // two corners per reward warp, summed by warp 0
+      if (EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1)) {
+        const Quat oq{obj[3], obj[4], obj[5], obj[6]};
+        const Quat gq{goal[3], goal[4], goal[5], goal[6]};
+        const float h = (float)P.cube_half_size;
+        float acc = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int kk = 2 * rw + q;
+          const float cx = (kk & 1) ? h : -h, cy = (kk & 2) ? h : -h, cz = (kk & 4) ? h : -h;
+          float ax, ay, az, bx, by, bz;
+          quat_rotate(oq, cx, cy, cz, ax, ay, az);
+          quat_rotate(gq, cx, cy, cz, bx, by, bz);
+          const float dd = norm3((obj[0] + ax) - (gx + bx), (obj[1] + ay) - (gy + by), (obj[2] + az) - (gz + bz));
+          acc = acc + lgsk(dd, s_coef[C_KP_SCALE], s_coef[C_KP_EPS]);
+        }
+        s_part[8 + rw][env] = acc;
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four reward warps
@@ -455,7 +465,8 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - s_part[7][env]));
       const bool kp_on = EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1);
       const float terms[7] = {s_part[0][env], s_part[1][env], s_part[2][env], s_part[5][env], t_delta, s_part[3][env],
-                              kp_on ? s_part[8][env] : 0.0f};
+                              kp_on ? s_coef[C_KP_W] * ((((s_part[8][env] + s_part[9][env]) + s_part[10][env]) + s_part[11][env]) * 0.125f)
+                                    : 0.0f};
       float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order (the extension term last)
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
@@ -622,22 +633,6 @@ __device__ __forceinline__ void tile_scan_finish(LgControl* ctl, uint64_t* statu
   ex_a = s_ex[0]; ex_b = s_ex[1];
 }
 
-// Cold path of the pre-physics kernel, kept out of line so that the no-reset step fetches and
-// executes none of the sampler / Philox code (trifinger_env.py:373-440).
-__device__ __noinline__ void reset_cold(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
-                                        bool f_reset, bool f_goal, int64_t rank_reset, int64_t rank_goal,
-                                        uint64_t epoch) {
-  if (f_reset) {
-    const DrawSource dr = make_draws(P, epoch, e, kPurposeReset, B.inject_reset_u, B.inject_reset_n, rank_reset);
-    reset_one_env(P, S, B, e, dr);
-  }
-  if (f_goal) {  // goal reset second, as in env_base.py:374-379
-    const DrawSource dr = make_draws(P, epoch, e, kPurposeGoal, B.inject_goal_u, B.inject_goal_n, rank_goal);
-    B.goal_reset[e] = 0;  // trifinger_env.py:427
-    apply_goal_sample(P, S, B, e, dr);
-  }
-}
-
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): one thread moves a whole contiguous tile slab -------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -719,7 +714,11 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     }
   }
   uint8_t flag_r = 0, flag_g = 0;
-  if (live) { flag_r = B.reset[e]; flag_g = B.goal_reset[e]; }
+  if (live) {
+    flag_r = B.reset[e]; flag_g = B.goal_reset[e];
+    if (B.force_reset) flag_r |= B.force_reset[e];             // `_reset_buf |= mask` folded into the pass
+    if (B.force_goal_reset) flag_g |= B.force_goal_reset[e];
+  }
   pdl_launch_dependents();
   if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
   if (tile == 0 && tid == NT - 1 && P.use_device_clock) {
@@ -772,12 +771,15 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     if (P.dr_activate && P.dr_action_sigma != 0.0f) {  // extension (no reference code): Gaussian action noise
       const uint64_t genv = (uint64_t)(P.env_offset + e);
 #pragma unroll
-      for (int c = 0; c < A; ++c) {
-        const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, 0x41435400u + c, epoch},
+      for (int c4 = 0; c4 < A; c4 += 4) {   // one Philox block -> four normals -> four action columns
+        const U4 r = philox4x32_10(U4{(uint32_t)genv, (uint32_t)(genv >> 32) ^ kPurposeNoise, 0x41435400u + c4, epoch},
                                    (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-        float n0, n1;
-        box_muller(r.x, r.y, n0, n1);
-        act[c] = act[c] + P.dr_action_sigma * n0;
+        float n[4];
+        box_muller(r.x, r.y, n[0], n[1]);
+        box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c4 + q < A) act[c4 + q] = act[c4 + q] + P.dr_action_sigma * n[q];
       }
     }
     if (P.clip_input_actions) {   // the wrapper's clamp (wrappers/vec_task.py:162)
@@ -792,9 +794,42 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
 #pragma unroll
     for (int c = 0; c < A; ++c) s_act[tid * A + c] = act[c];
   }
-  // ---- resets (cold) -------------------------------------------------------------------------------
-  if (f_reset || f_goal)
-    reset_cold(P, S, B, e, f_reset, f_goal, (int64_t)ex_a + t.rank_a, (int64_t)ex_b + t.rank_b, (uint64_t)epoch);
+  // ---- resets (trifinger_env.py:373-440) -----------------------------------------------------------------
+  // Block-uniform branch: a tile without flagged envs neither fetches nor executes sampler code.  The flagged envs
+  // are listed in shared memory by their rank in the tile, then each WARP runs two of the eight reset sub-tasks over
+  // that list (lane = listed env): uniform control flow, and a serial chain of ~2 Philox blocks per warp instead of
+  // ten per resetting thread.
+  if ((t.total_a | t.total_b) != 0) {
+    __shared__ uint16_t s_reset_list[E], s_goal_list[E];
+    if (f_reset) s_reset_list[t.rank_a] = (uint16_t)(tid | (f_goal ? 0x8000 : 0));
+    if (f_goal) s_goal_list[t.rank_b] = (uint16_t)tid;
+    __syncthreads();
+    const int na = (int)t.total_a, nb = (int)t.total_b;
+    auto run_sub = [&](int sub, int first, int step) {
+#pragma unroll 1
+      for (int r = first; r < na; r += step) {
+        const int ent = s_reset_list[r], local = ent & 0x7fff;
+        const int64_t env = e0 + local;
+        const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeReset, B.inject_reset_u, B.inject_reset_n,
+                                         (int64_t)ex_a + r);
+        reset_subtask(P, S, B, env, sub, dr, (ent & 0x8000) != 0, s_dof + local * 18);
+      }
+    };
+    // the two long sub-tasks (object pose: 2 Philox blocks, sqrt, 2 sincos; goal: 2-3 blocks, Box-Muller, normalise)
+    // take two warps each, the six short ones (joint blocks 0..4, bookkeeping) are spread over the four warps
+    run_sub(warp < 2 ? 5 : 6, tid & 63, 64);
+    run_sub(warp, lane, 32);                                   // joint blocks 0..3
+    if (warp < 2) run_sub(warp == 0 ? 4 : 7, lane, 32);        // joint block 4, bookkeeping
+#pragma unroll 1
+    for (int r = tid; r < nb; r += NT) {   // goal resets second, as in env_base.py:374-379
+      const int64_t env = e0 + s_goal_list[r];
+      const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
+                                       (int64_t)ex_b + r);
+      B.goal_reset[env] = 0;  // trifinger_env.py:427
+      apply_goal_sample(P, S, B, env, dr);
+    }
+    __syncthreads();   // the torque and goal-movement code below reads rows other lanes have just rewritten
+  }
   // ---- moving goal (__update_goal_movement_pre, trifinger_env.py:1267-1277): every step the goal body's
   // angular velocity is re-imposed from the movement buffer (freshly sampled above for envs that reset)
   if (P.goal_rotation && live) {
@@ -804,8 +839,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   }
   // ---- action -> torque (trifinger_env.py:442-498), on the post-reset joint state ---------------
   if (want_torque && live) {
-    const bool dof_rewritten = f_reset && P.robot_reset != LG_RESET_NONE;
-    torque_one_env(P, act, dof_rewritten ? S.dof_state + e * 18 : s_dof + tid * 18, s_tq + tid * 9);
+    torque_one_env(P, act, s_dof + tid * 18, s_tq + tid * 9);   // resets mirrored their joint rows into s_dof
   }
   if (full_tile) {
     fence_async_proxy();           // generic-proxy writes to the slabs -> visible to the bulk-copy engine

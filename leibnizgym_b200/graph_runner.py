@@ -27,7 +27,8 @@ from .synthetic import StateSequence
 
 class GraphRunner:
     def __init__(self, env: TrifingerEnv, ring: StateSequence, rotate_outputs: bool = True,
-                 inject_reset_masks: Optional[torch.Tensor] = None, device_clock: bool = True):
+                 inject_reset_masks: Optional[torch.Tensor] = None, device_clock: bool = True,
+                 inject_goal_masks: Optional[torch.Tensor] = None):
         assert ring.dof_state.is_cuda, "the ring must be device resident"
         self.env, self.ring = env, ring
         self.R = ring.num_steps
@@ -36,7 +37,10 @@ class GraphRunner:
         self.obs_slots = torch.zeros((self.R if rotate_outputs else 1, N, env.get_obs_dim()), device=dev)
         sd = env.get_state_dim()
         self.state_slots = torch.zeros((self.R if rotate_outputs else 1, N, sd), device=dev) if sd else None
-        self.reset_masks = inject_reset_masks  # [R, N] bool or None: OR-ed into _reset_buf before each step
+        # [R, N] bool or None: OR-ed into _reset_buf / _goal_reset_buf at the start of each step, by lg_pre_physics
+        # itself (LgBuffers.force_reset / force_goal_reset) — no separate pass over the flags
+        self.reset_masks = inject_reset_masks
+        self.goal_masks = inject_goal_masks
         self.P = nat.LgParams.from_buffer_copy(env._P)
         self.P.use_device_clock = int(device_clock)
         self.P.fuse_bookkeeping = 1
@@ -57,6 +61,10 @@ class GraphRunner:
             b.states = self.state_slots[o].data_ptr() if self.state_slots is not None else None
             b.obs_clipped = b.states_clipped = None
             b.term_rewards = None
+            # the pre-physics pass of step t runs on the buffers of slot t-1 (see _launch_step): masks of step t
+            nxt = (t + 1) % self.R
+            b.force_reset = self.reset_masks[nxt].data_ptr() if self.reset_masks is not None else None
+            b.force_goal_reset = self.goal_masks[nxt].data_ptr() if self.goal_masks is not None else None
             self._B.append(b)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.steps_per_graph = 0
@@ -68,8 +76,6 @@ class GraphRunner:
         s = t % self.R
         prev = (t - 1) % self.R
         if not post_only:
-            if self.reset_masks is not None:
-                self.env._reset_buf.logical_or_(self.reset_masks[s])
             # resets write into the tensors the simulator consumes next (slot of the previous state)
             nat.check(self.lib.lg_pre_physics(self.P, self._S[prev], self._B[prev],
                                               self.ring.action[s].data_ptr(), stream), "lg_pre_physics")
