@@ -167,6 +167,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   __shared__ float s_coef[C_COUNT];
   __shared__ float s_part[12][E];       // sub-task results of the reward warps
   __shared__ float s_stat[LG_NUM_STATS][E + 1];
+  __shared__ float s_noise[EXT ? L::OBS : 1][EXT ? E + 1 : 1];   // extension: standard normals of the obs columns
 
   const int tid = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * E;
@@ -279,6 +280,32 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     float* h = s_hist + renv * HS + rw * 4;
     h[0] = hprev.x; h[1] = hprev.y; h[2] = hprev.z; h[3] = hprev.w;
   }
+  // extension (DR observation noise): the tile's standard normals, generated by ALL threads while the loads are in
+  // flight — one Philox block + two Box-Muller pairs per (column, group of 4 envs by GLOBAL index), so the stream
+  // does not depend on tiling or sharding.  Columns with sigma = 0 are skipped.
+  if (EXT && P.dr_activate) {
+    const uint64_t base = (uint64_t)(P.env_offset + e0);
+    const uint64_t g0 = base >> 2;
+    const int ngroups = (int)(((base + E - 1) >> 2) - g0) + 1;
+    const uint32_t noise_epoch = __float_as_uint((REWARD && P.use_device_clock) ? __ldg(B.reward_coef + C_NOISE_EPOCH)
+                                                                                  : CF.v[C_NOISE_EPOCH]);
+    for (int i = tid; i < L::OBS * ngroups; i += kPostThreads) {
+      const int col = i / ngroups, g = i - col * ngroups;
+      if (__ldg(B.scale_table + 3 * LG_MAX_STATE_DIM + col) != 0.0f) {
+        const uint64_t grp = g0 + g;
+        const U4 r = philox4x32_10(U4{(uint32_t)grp, (uint32_t)(grp >> 32) ^ kPurposeNoise, (uint32_t)col, noise_epoch},
+                                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        float n[4];
+        box_muller(r.x, r.y, n[0], n[1]);
+        box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t local = (int64_t)(4 * grp + q) - (int64_t)base;
+          if (local >= 0 && local < E) s_noise[col][local] = n[q];
+        }
+      }
+    }
+  }
   if (front && stage) {
     float* dst = stage + env_first * stage_stride;
     if (full) {
@@ -319,8 +346,6 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     // wrapper's clamp is fused in, else of the scaled values
     uint16_t* stb = (EXT && ASYM && B.states_bf16) ? B.states_bf16 + e0 * L::STATE + st_off : nullptr;
     uint16_t* obb = (EXT && B.obs_bf16) ? B.obs_bf16 + e0 * L::OBS + ob_off : nullptr;
-    uint64_t noise_group = ~0ull;     // envs come in groups of 4 (by GLOBAL index): one Philox block -> 4 normals
-    float nz0 = 0.0f, nz1 = 0.0f, nz2 = 0.0f, nz3 = 0.0f;
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
       const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
@@ -334,17 +359,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
         if (to_obs) {
           float ov = sv;
           if (noisy) {
-            const uint64_t genv = (uint64_t)(P.env_offset + e0 + env_first + k), grp = genv >> 2;
-            if (grp != noise_group) {
-              noise_group = grp;
-              const U4 r = philox4x32_10(U4{(uint32_t)grp, (uint32_t)(grp >> 32) ^ kPurposeNoise, (uint32_t)dcol,
-                                            __float_as_uint(s_coef[C_NOISE_EPOCH])},
-                                         (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-              box_muller(r.x, r.y, nz0, nz1);
-              box_muller(r.z, r.w, nz2, nz3);
-            }
-            const int which = (int)(genv & 3);
-            const float n0 = which == 0 ? nz0 : which == 1 ? nz1 : which == 2 ? nz2 : nz3;
+            const float n0 = s_noise[dcol][env_first + k];   // generated before the barrier, see above
             ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
           }
           ob[k * L::OBS] = ov;
