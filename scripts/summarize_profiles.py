@@ -128,7 +128,8 @@ if __name__ == "__main__":
     for n in (65536, 262144, 1048576):
         copy_json(f"bench_c2_{n}_{R}.json", f"{R}_bench_c2_{n}envs.json")
     for g in (2, 4, 8):
-        copy_json(f"bench_c2_{g}gpu_{R}.json", f"{R}_bench_c2_{g}gpu.json")
+        for wl in ("c2", "c4", "c5"):
+            copy_json(f"bench_{wl}_{g}gpu_{R}.json", f"{R}_bench_{wl}_{g}gpu.json")
     smi = os.path.join(OUT, f"smi_{R}.csv")
     if os.path.exists(smi):
         shutil.copy(smi, os.path.join(PROF, f"{R}_nvidia_smi.csv"))
