@@ -345,6 +345,8 @@ class TrifingerEnv(IsaacEnvBase):
         b.applied_torque, b.term_rewards = p(self._applied_torque), p(self._term_rewards)
         b.step_stats = p(self._step_stats)
         b.obs_bf16, b.states_bf16 = p(self._obs_bf16), p(self._states_bf16)
+        fr, fg = getattr(self, "_force_masks", (None, None))
+        b.force_reset, b.force_goal_reset = p(fr), p(fg)
         b.reset_ids, b.goal_reset_ids, b.counts = p(self._reset_ids), p(self._goal_reset_ids), p(self._counts)
         b.robot_indices, b.reset_root_indices, b.goal_root_indices = p(self._robot_indices), p(self._reset_root_indices), p(self._goal_root_indices)
         b.scan_status, b.control = p(self._scan_status), p(self._control)
@@ -380,6 +382,18 @@ class TrifingerEnv(IsaacEnvBase):
         if clip_actions is not None:
             self._P.clip_actions, self._P.clip_input_actions = float(clip_actions), 1
         self._bind()
+
+    def set_forced_resets(self, reset_mask: Optional[torch.Tensor] = None, goal_reset_mask: Optional[torch.Tensor] = None):
+        """Masks OR-ed into `_reset_buf` / `_goal_reset_buf` at the start of every following step, inside the
+        pre-physics pass itself — what `env._reset_buf |= mask` between steps does (tests, reset-heavy workloads),
+        without a separate pass over the flags.  [N] bool device tensors, kept alive here; None switches one off."""
+        for m in (reset_mask, goal_reset_mask):
+            if m is not None and (m.dtype != torch.bool or m.device != self._torch_device or m.numel() != self.num_instances
+                                  or not m.is_contiguous()):
+                raise ValueError("forced-reset masks must be contiguous [num_instances] bool tensors on the env's device")
+        self._force_masks = (reset_mask, goal_reset_mask)
+        self._B.force_reset = nat.ptr(reset_mask)
+        self._B.force_goal_reset = nat.ptr(goal_reset_mask)
 
     def enable_bf16_outputs(self):
         """Also emit bfloat16 copies of the (clipped, when enabled) observations and states from the same pass, for

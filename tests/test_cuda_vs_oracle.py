@@ -395,3 +395,37 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
                          sim=SyntheticSim(make_sequence(13, 2, N + 1).to("cuda:0"), "cuda:0"))
     with pytest.raises(ValueError):
         other.load_checkpoint(path)
+
+
+def test_forced_reset_masks_equal_or_into_the_flag_buffers():
+    """LgBuffers.force_reset / force_goal_reset (masks folded into lg_pre_physics) == `env._reset_buf |= mask` between steps."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import bernoulli_masks, make_sequence
+    N, T = 5000, 6
+    cfg = difficulty_config(4, N, seed=31)
+    seq = make_sequence(9, T, N)
+    rm = bernoulli_masks(3, T, N, 0.3, device="cuda:0")
+    gm = bernoulli_masks(4, T, N, 0.1, device="cuda:0")
+    a = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    b = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    a.reset()
+    b.reset()
+    for t in range(1, T):
+        a._reset_buf |= rm[t]
+        a._goal_reset_buf |= gm[t]
+        b.set_forced_resets(rm[t].contiguous(), gm[t].contiguous())
+        oa = a.step(seq.action[t].cuda())
+        ob = b.step(seq.action[t].cuda())
+        assert torch.equal(a.reset_env_ids, b.reset_env_ids) and torch.equal(a.goal_reset_env_ids, b.goal_reset_env_ids)
+        assert len(a.reset_env_ids) > 0.2 * N
+        for x, y in zip(oa[:3], ob[:3]):
+            assert torch.equal(x, y)
+        assert torch.equal(a.states_buf, b.states_buf) and torch.equal(a._object_goal_poses_buf, b._object_goal_poses_buf)
+        assert torch.equal(a._dof_state, b._dof_state) and torch.equal(a._reset_buf, b._reset_buf)
+    b.set_forced_resets(None, None)
+    b.step(seq.action[1].cuda())
+    assert len(b.reset_env_ids) == 0
+    with pytest.raises(ValueError):
+        b.set_forced_resets(torch.zeros(N, dtype=torch.uint8, device="cuda:0"))
