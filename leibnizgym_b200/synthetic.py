@@ -70,7 +70,7 @@ def _unit_quat(g, shape, device):
 
 
 def make_sequence(seed: int, num_steps: int, num_envs: int, device: str = "cpu",
-                  first_env: int = 0) -> StateSequence:
+                  first_env: int = 0, action_dim: int = NUM_DOF) -> StateSequence:
     """Seeded synthetic state sequence (distributions of SURVEY.md §8(d)).
 
     `first_env` offsets the seed so that a shard [first_env, first_env+num_envs)
@@ -106,7 +106,7 @@ def make_sequence(seed: int, num_steps: int, num_envs: int, device: str = "cpu",
 
     dof_force = -0.36 + 0.72 * torch.rand(T, N, NUM_DOF, **kw)
     ft_sensors = 0.3 * torch.randn(T, N, 18, **kw)
-    action = -1.0 + 2.0 * torch.rand(T, N, NUM_DOF, **kw)
+    action = -1.0 + 2.0 * torch.rand(T, N, action_dim, **kw)   # 18 for the position_impedance command mode
     return StateSequence(dof_state, root_state, rigid_body.contiguous(), dof_force, ft_sensors, action)
 
 

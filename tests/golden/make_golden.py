@@ -84,7 +84,7 @@ def run_scenario(name: str, record_draws: bool) -> dict:
     from ref_harness import DrawRecorder, build_reference_env, reward_terms_of, stash_goal_before_movement
     sc = SCENARIOS[name]
     N, T, seed = sc["N"], sc["T"], sc["seed"]
-    seq = make_sequence(seed, T, N)
+    seq = make_sequence(seed, T, N, action_dim=sc.get("action_dim", 9))
     reset_masks = bernoulli_masks(seed, T, N, sc.get("reset_p", 0.0))
     goal_masks = bernoulli_masks(seed + 1, T, N, sc.get("goal_reset_p", 0.0))
     if sc.get("plant_goal_rows"):   # what a simulator integrating the goal body would leave in its root rows

@@ -78,6 +78,9 @@ SCENARIOS = {
     "moving_goal": dict(
         N=24, T=7, seed=1010, reset_p=0.1, goal_reset_p=0.2, plant_goal_rows=True,
         config=_cfg(4, 24, True, 1010, goal_movement={"rotation": {"activate": True, "rate_magnitude": 0.5}})),
+    # variable-impedance command mode: 18-dim action (position + stiffness), 50-dim obs, 122-dim states
+    "d3_impedance": dict(N=20, T=5, seed=1011, reset_p=0.2, action_dim=18,
+                         config=_cfg(3, 20, True, 1011, command_mode="position_impedance")),
     "d6_sym": dict(N=20, T=5, seed=1009, reset_p=0.25, goal_reset_p=0.25,
                    config=_cfg(6, 20, False, 1009, normalize_action=False,
                                reset_distribution={"object_initial_state": {"type": "none"}})),
