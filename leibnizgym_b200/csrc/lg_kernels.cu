@@ -696,7 +696,10 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   __shared__ int s_tile;
   __shared__ uint32_t s_wa[NT / 32], s_wb[NT / 32];
   const int tid = threadIdx.x;
-  pdl_wait();
+  // Launched programmatically after lg_post_physics (see pdl_mode): what this kernel reads before pdl_wait() below
+  // must not be written by that kernel.  The control block (epoch, ticket) is only written by this kernel's own
+  // previous launch, the action and the joint state by the caller / simulator — all complete before the preceding
+  // post-physics pass was allowed past its own dependency wait.
   // every thread reads the epoch before the tile publishes anything, so the last tile may advance it
   const uint32_t epoch = ld_volatile_u32(&B.control->scan_epoch);
   int tile = blockIdx.x;
@@ -728,6 +731,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
       for (int c = 0; c < 18; ++c) s_dof[tid * 18 + c] = S.dof_state[e * 18 + c];
     }
   }
+  pdl_wait();   // the flags, counters and statistics below are results of the preceding post-physics pass
   uint8_t flag_r = 0, flag_g = 0;
   if (live) {
     flag_r = B.reset[e]; flag_g = B.goal_reset[e];

@@ -1,8 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() { # label, args
-  timeout 300 python bench.py ${@:2} --no-cpu --e2e-steps 8 > gpurun_out/v.json 2>gpurun_out/v.err || tail -3 gpurun_out/v.err
+run() { # label, env, args
+  env $2 timeout 300 python bench.py ${@:3} --no-cpu --e2e-steps 8 > gpurun_out/v.json 2>gpurun_out/v.err || tail -3 gpurun_out/v.err
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/v.json").read().strip().splitlines()[-1])
@@ -10,15 +10,11 @@ print("$1", "step us %.2f" % (d["ms_per_step"]*1e3), "post us %.2f" % d["rooflin
 PY
 }
 for i in 1 2; do
-  for v in base new; do
-    cp ab/$v.so leibnizgym_b200/libleibniz_b200.so
-    run c2_$v --steps 8192 --warmup 256
-  done
-done
 for v in base new; do
   cp ab/$v.so leibnizgym_b200/libleibniz_b200.so
-  run c4_$v --workload c4 --steps 2048 --warmup 64
-  run c5_$v --workload c5 --steps 2048 --warmup 64
+  run c2_${v} X=0 --steps 8192 --warmup 256
+  run c5_${v} X=0 --workload c5 --steps 2048 --warmup 64
+  run c3ref_${v} X=0 --workload c3ref --steps 1024 --warmup 64
+done
 done
 cp ab/new.so leibnizgym_b200/libleibniz_b200.so
-timeout 600 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -4
