@@ -1084,8 +1084,9 @@ int sm_count() {
   return n;
 }
 
-// bit 0: pre-physics kernel launched programmatically, bit 1: post-physics kernel.  Measured on B200 at
-// 16k envs: post only 12.7 us/step, none 13.1, both 14.1 — the pre kernel gains nothing from starting early.
+// bit 0: pre-physics kernel launched programmatically, bit 1: post-physics kernel.  Measured on B200 (us/step):
+// 16k envs, no resets: post only 11.5-11.7, both 11.4-11.5, none 11.9; 30 % resets: post only 17.5, both 21.6 —
+// a long pre-physics pass should not have the post pass's CTAs parked on the SMs, so the default is post only.
 int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : env_int("LG_PDL", 2); return m; }
 
 // Launch with programmatic stream serialisation (PDL) unless LG_NO_PDL is set.
