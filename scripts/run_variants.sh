@@ -1,6 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+cp ab/new.so leibnizgym_b200/libleibniz_b200.so
+timeout 900 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -6
 run() { # label, env, args
   env $2 timeout 300 python bench.py ${@:3} --no-cpu --e2e-steps 8 > gpurun_out/v.json 2>gpurun_out/v.err || tail -3 gpurun_out/v.err
   python - <<PY
@@ -13,8 +15,13 @@ for i in 1 2; do
 for v in base new; do
   cp ab/$v.so leibnizgym_b200/libleibniz_b200.so
   run c2_${v} X=0 --steps 8192 --warmup 256
+done
+done
+for v in base new; do
+  cp ab/$v.so leibnizgym_b200/libleibniz_b200.so
   run c5_${v} X=0 --workload c5 --steps 2048 --warmup 64
   run c3ref_${v} X=0 --workload c3ref --steps 1024 --warmup 64
-done
+  run c4_${v} X=0 --workload c4 --steps 2048 --warmup 64
+  run c2sym_${v} X=0 --workload c2sym --steps 4096 --warmup 64
 done
 cp ab/new.so leibnizgym_b200/libleibniz_b200.so
