@@ -346,15 +346,18 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     // wrapper's clamp is fused in, else of the scaled values
     uint16_t* stb = (EXT && ASYM && B.states_bf16) ? B.states_bf16 + e0 * L::STATE + st_off : nullptr;
     uint16_t* obb = (EXT && B.obs_bf16) ? B.obs_bf16 + e0 * L::OBS + ob_off : nullptr;
+    // outputs go out with streaming stores (st.global.cs): nothing on the device reads them again before the
+    // learner does, and evict-first keeps them from displacing the simulator rows in L2 (measured: 84.0 -> 80.3 us
+    // at 262 144 envs, 7.25 -> 7.15 us at 16 384)
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
       const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
       if (FULLC || k < cnt) {
         if (ASYM) {
-          st[k * L::STATE] = sv;
+          __stcs(st + k * L::STATE, sv);
           const float svc = CLIP ? fminf(fmaxf(sv, -clip), clip) : sv;
-          if (CLIP) stc[k * L::STATE] = svc;
-          if (EXT && stb) stb[k * L::STATE] = to_bf16(svc);
+          if (CLIP) __stcs(stc + k * L::STATE, svc);
+          if (EXT && stb) __stcs(stb + k * L::STATE, to_bf16(svc));
         }
         if (to_obs) {
           float ov = sv;
@@ -362,10 +365,10 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
             const float n0 = s_noise[dcol][env_first + k];   // generated before the barrier, see above
             ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
           }
-          ob[k * L::OBS] = ov;
+          __stcs(ob + k * L::OBS, ov);
           const float ovc = CLIP ? fminf(fmaxf(ov, -clip), clip) : ov;
-          if (CLIP) obc[k * L::OBS] = ovc;
-          if (EXT && obb) obb[k * L::OBS] = to_bf16(ovc);
+          if (CLIP) __stcs(obc + k * L::OBS, ovc);
+          if (EXT && obb) __stcs(obb + k * L::OBS, to_bf16(ovc));
         }
       }
     }
