@@ -297,12 +297,6 @@ def run_gpu(args, wl):
     if args.l2_fetch:
         from leibnizgym_b200 import _native as nat
         nat.check(nat.load().lg_set_l2_fetch_granularity(args.l2_fetch), "lg_set_l2_fetch_granularity")
-    if os.environ.get("LG_PDL_EARLY") == "0":
-        import ctypes
-        from leibnizgym_b200 import _native as nat
-        fn = nat.load().lg_debug_set_pdl_early
-        fn.argtypes, fn.restype = [ctypes.c_int], ctypes.c_int
-        assert fn(0) == 0
     N = wl["envs"]
     K, W = args.steps, max(args.warmup, 3)
     R = args.ring

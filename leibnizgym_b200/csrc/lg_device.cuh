@@ -32,10 +32,6 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
-               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

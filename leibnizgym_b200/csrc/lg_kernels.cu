@@ -25,8 +25,7 @@ namespace lg {
 // griddepcontrol.wait then blocks until the predecessor's grid has completed and its writes are
 // visible.  Two ~2 us launches per step make this worth ~1/4 of the step time at 16k envs.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ int g_pdl_early = 1;
-__device__ __forceinline__ void pdl_launch_dependents() { if (g_pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // =========================================================================================
 // post-physics: one CTA = one tile of E envs, 4 threads per env
@@ -741,7 +740,6 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     if (B.force_reset) flag_r |= B.force_reset[e];             // `_reset_buf |= mask` folded into the pass
     if (B.force_goal_reset) flag_g |= B.force_goal_reset[e];
   }
-  pdl_launch_dependents();
   if (tile == 0 && tid < LG_NUM_STATS && B.step_stats) B.step_stats[tid] = 0.0;  // accumulated by lg_post_physics
   if (tile == 0 && tid == NT - 1 && P.use_device_clock) {
     // device clock: advance the frame counter and publish the reward coefficients of the coming
@@ -863,6 +861,11 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   if (want_torque && live) {
     torque_one_env(P, act, s_dof + tid * 18, s_tq + tid * 9);   // resets mirrored their joint rows into s_dof
   }
+  // The post-physics pass may start launching now.  Triggering earlier parks its CTAs (which fill the register file)
+  // next to this kernel's one warp per scheduler and slows the latency chain above; measured, us/step at 16k envs /
+  // 30 % resets: right after the flag loads 11.50 / 16.95, after the slab wait 11.38 / 16.83, here 11.28 / 16.50,
+  // no explicit trigger 11.98 / 17.24.
+  pdl_launch_dependents();
   if (full_tile) {
     fence_async_proxy();           // generic-proxy writes to the slabs -> visible to the bulk-copy engine
     __syncthreads();
@@ -1183,7 +1186,6 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
 extern "C" {
 
 int lg_version(void) { return LG_VERSION; }
-int lg_debug_set_pdl_early(int on) { return cudaMemcpyToSymbol(lg::g_pdl_early, &on, sizeof(int)) == cudaSuccess ? LG_OK : check_launch("memcpyToSymbol"); }
 int lg_set_l2_fetch_granularity(int bytes) {
   if (bytes != 32 && bytes != 64 && bytes != 128) return fail(LG_ERR_BAD_ARG, "granularity must be 32, 64 or 128");
   if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes) != cudaSuccess) return check_launch("cudaDeviceSetLimit");
