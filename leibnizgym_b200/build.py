@@ -38,7 +38,8 @@ def needs_build() -> bool:
     if not os.path.exists(OUTPUT):
         return True
     out_m = os.path.getmtime(OUTPUT)
-    deps = SOURCES + [os.path.join(HERE, "csrc", "lg_device.cuh"), os.path.join(ROOT, "include", "leibniz_b200.h")]
+    csrc = os.path.join(HERE, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", "leibniz_b200.h")]
     return any(os.path.getmtime(d) > out_m for d in deps)
 
 

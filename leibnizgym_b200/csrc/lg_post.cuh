@@ -1,0 +1,560 @@
+// post-physics pass of the TriFinger MDP hot path (sm_100a): obs/states fill + scale_transform, six reward terms,
+// termination, step counters / timeouts / dones, episode statistics — one lane per output column.
+// Included by lg_kernels.cu (single translation unit).  Reference paths are relative to /root/reference/leibnizgym/.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "lg_device.cuh"
+
+namespace lg {
+
+
+// Programmatic dependent launch (PDL): a kernel launched with programmatic stream serialisation may
+// begin (CTA scheduling, parameter fetch, address set-up) before its predecessor has finished;
+// griddepcontrol.wait then blocks until the predecessor's grid has completed and its writes are
+// visible.  Two ~2 us launches per step make this worth ~1/4 of the step time at 16k envs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// =========================================================================================
+// post-physics: one CTA = one tile of E envs, 4 threads per env
+// =========================================================================================
+constexpr int kPostThreads = 256;
+
+template <int A, bool ASYM>
+struct Layout {
+  static constexpr int OBS = 32 + A;              // q 9 | qdot 9 | object pose 7 | goal pose 7 | action A
+  static constexpr int STATE = OBS + 72;          // + object vel 6 | fingertips 39 | torque 9 | wrench 18
+  static constexpr int ROW = ASYM ? STATE : OBS;  // floats per env in the staged tile
+  static constexpr int OFF_OBJ = 18, OFF_GOAL = 25, OFF_ACT = 32;
+  static constexpr int OFF_OBJVEL = OBS, OFF_TIPS = OBS + 6, OFF_TORQUE = OBS + 45, OFF_FT = OBS + 54;
+};
+
+// coefficient slots computed once per CTA (python-float arithmetic of the reward modules)
+enum Coef { C_REACH = 0, C_MOVE, C_DIST, C_ROT_SCALE, C_ROT_SCHED, C_ROT_W, C_DELTA_RAMP, C_DELTA_W,
+            C_OBJMOVE, C_DT, C_DT_RCP, C_POS_TOL, C_ROT_TOL, C_BONUS, C_KP_W, C_KP_SCALE, C_KP_EPS, C_NOISE_EPOCH,
+            C_COUNT };
+
+__host__ __device__ inline double sched_gate(const LgRewardTerm& t, double T) {  // rewards.py:56-60
+  if (t.sched_start != t.sched_end) return (t.sched_start <= T && T <= t.sched_end) ? 1.0 : 0.0;
+  return 1.0;
+}
+__host__ __device__ inline double sched_ramp(const LgRewardTerm& t, double T) {  // rewards.py:14-17, :169-172
+  if (t.sched_start != t.sched_end) {
+    const double v = (T - t.sched_start) / (t.sched_end - t.sched_start);
+    return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+  }
+  return 1.0;
+}
+// The reward modules' Python-float arithmetic for env_steps_count = T.  Same code on host and device
+// (IEEE double in both places), so the two clock modes produce identical coefficients.
+__host__ __device__ inline void compute_coefs(const LgParams& P, double T, float* c) {
+  const LgRewardTerm* t = P.terms;
+  c[C_REACH] = (float)(t[0].weight * sched_gate(t[0], T));             // rewards.py:235
+  c[C_MOVE] = (float)t[1].weight;                                       // rewards.py:263
+  c[C_DIST] = (float)((t[2].weight * P.dt) * sched_gate(t[2], T));     // rewards.py:63
+  c[C_ROT_SCALE] = (float)t[3].scale;                                   // rewards.py:137
+  c[C_ROT_SCHED] = (float)(sched_gate(t[3], T) * P.dt);
+  c[C_ROT_W] = (float)t[3].weight;                                      // rewards.py:139
+  c[C_DELTA_RAMP] = (float)sched_ramp(t[4], T);                         // rewards.py:182
+  c[C_DELTA_W] = (float)t[4].weight;                                    // rewards.py:184
+  c[C_OBJMOVE] = (float)t[5].weight;                                    // rewards.py:91
+  c[C_DT] = (float)P.dt;
+  c[C_DT_RCP] = 1.0f / (float)P.dt;                                     // IEEE division: correctly rounded
+  c[C_POS_TOL] = (float)P.position_tolerance;
+  c[C_ROT_TOL] = (float)P.orientation_tolerance;
+  c[C_BONUS] = (float)P.success_bonus;
+  c[C_KP_W] = (float)(t[6].weight * P.dt);
+  c[C_KP_SCALE] = (float)t[6].scale;
+  c[C_KP_EPS] = (float)t[6].eps;
+  // step identifier of the domain-randomisation noise stream: env_steps_count itself (bit pattern, not a value)
+  union { uint32_t u; float f; } bits;
+  bits.u = (uint32_t)(unsigned long long)T;
+  c[C_NOISE_EPOCH] = bits.f;
+}
+static_assert(C_COUNT <= LG_NUM_COEF, "LgCoef too small");
+
+// Fast division by a per-column constant: q = x*r, q' = fma(fma(-q, span, x), r, q) with r = fp32(1/span)
+// correctly rounded (Markstein).  Contract, verified exhaustively by lg_selftest_division over all 2^32
+// numerators for every span the env uses:
+//   * 2^-100 <= |x| < 2^100 : bit-identical to IEEE x / span;
+//   * x = +-0                : 0 (a negative zero comes out as +0);
+//   * 0 < |x| < 2^-100       : within 1 ulp (the residual may be subnormal);
+//   * |x| >= 2^100, inf      : flagged through `amax`; the caller redoes the column with __fdiv_rn.
+__device__ __forceinline__ float div_by_const(float num, float span, float rcp, float& amax) {
+  const float q = num * rcp;
+  const float r = __fmaf_rn(-q, span, num);
+  amax = fmaxf(amax, fabsf(num));
+  return __fmaf_rn(r, rcp, q);
+}
+constexpr float kDivSafeMax = 1.2676506e30f;  // 2^100
+
+// bfloat16 bits of a float, round-to-nearest-even (what torch's .to(torch.bfloat16) does)
+__device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+
+// Cold path: re-emit one lane's output column with IEEE division (only when a numerator left the fast
+// division's window).  Re-reads the source so the hot path keeps its registers.
+template <int STATE, int OBS, bool ASYM>
+__device__ __noinline__ void output_exact(const LgParams& P, const LgBuffers& B, const float* src, int stride, int cnt,
+                                          int64_t env0, int dcol) {
+  const float centre = P.scale_centre[dcol], span = P.scale_span[dcol], clip = P.clip_obs;
+  for (int k = 0; k < cnt; ++k) {
+    const int64_t e = env0 + k;
+    const float raw = src[(int64_t)k * stride];
+    const float v = P.normalize_obs ? __fdiv_rn(2.0f * (raw - centre), span) : raw;
+    const float vc = fminf(fmaxf(v, -clip), clip);
+    if (ASYM) B.states[e * STATE + dcol] = v;
+    if (dcol < OBS) B.obs[e * OBS + dcol] = v;
+    if (ASYM && B.states_clipped) B.states_clipped[e * STATE + dcol] = vc;
+    if (dcol < OBS && B.obs_clipped) B.obs_clipped[e * OBS + dcol] = vc;
+    if (ASYM && B.states_bf16) B.states_bf16[e * STATE + dcol] = to_bf16(B.states_clipped ? vc : v);
+    if (dcol < OBS && B.obs_bf16) B.obs_bf16[e * OBS + dcol] = to_bf16(B.obs_clipped ? vc : v);
+  }
+}
+
+// One lane = one OUTPUT column of the tile ("role"), walking over the envs of its part of the tile.
+// The role fixes, per lane and once per launch: the source pointer and row stride, the output column
+// with its scale constants, and where (if anywhere) the raw value is staged for the reward math.
+// The per-element code is then identical for every lane — no divergence although the lanes of a warp
+// read from seven different tensors — and free of index arithmetic:
+//     load   v[k] = src[k * stride]                       (all loads of the tile in flight at once)
+//     emit   states[k][dcol] = obs[k][dcol] = scale(v[k])  (compile-time row offsets)
+// Role order = output column order of the states row, except that the nine fingertip POSITION columns
+// come right after the observation columns: the lanes that feed obs, the reward staging and the next
+// history entry are then all in the first two warps of a part, and the other warps skip that code.
+template <int A, bool ASYM, int E>
+struct Roles {
+  static constexpr int OBS = 32 + A;
+  static constexpr int R_TIPPOS = OBS;                  // 9 roles
+  static constexpr int R_TIPREST = R_TIPPOS + 9;        // 30 roles (asymmetric only)
+  static constexpr int R_OBJVEL = R_TIPREST + 30;       // 6
+  static constexpr int R_FT = R_OBJVEL + 6;             // 18
+  static constexpr int R_TQ = R_FT + 18;                // 9
+  static constexpr int R_END = ASYM ? R_TQ + 9 : R_TIPREST;
+  static constexpr int LANES = R_END <= 64 ? 64 : 128;  // role lanes per tile part
+  static constexpr int PARTS = kPostThreads / LANES;    // the tile's envs are split over the parts
+  static constexpr int EP = E / PARTS;                  // envs per lane
+  static_assert(E % PARTS == 0 && E <= 32, "tile must split evenly; the reward math uses one lane per env");
+  static constexpr int FRONT = R_TIPREST;               // roles < FRONT may feed obs / staging / history
+  static_assert(R_END <= LANES, "more output columns than role lanes");
+};
+
+template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT>
+__global__ void __launch_bounds__(kPostThreads, 4)
+post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
+                    const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
+  using L = Layout<A, ASYM>;
+  using R = Roles<A, ASYM, E>;          // E envs per CTA
+  constexpr int EP = R::EP;
+  constexpr int HS = LG_HISTORY_COLS + 1;  // padded row: lane-per-env reads stay conflict free
+  // only what the reward terms read is staged in shared memory (raw, unscaled)
+  __shared__ float s_obj[E * 7];        // object pose
+  __shared__ float s_goal[E * 7];       // goal pose
+  __shared__ float s_tips[E * 9];       // fingertip positions
+  __shared__ float s_hist[E * HS];      // previous fingertip positions (9) + previous object pose (7)
+  __shared__ float s_coef[C_COUNT];
+  __shared__ float s_part[12][E];       // sub-task results of the reward warps
+  __shared__ float s_stat[LG_NUM_STATS][E + 1];
+  __shared__ float s_noise[EXT ? L::OBS : 1][EXT ? E + 1 : 1];   // extension: standard normals of the obs columns
+
+  const int tid = threadIdx.x;
+  const int64_t e0 = (int64_t)blockIdx.x * E;
+  const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
+
+  // ---- role of this lane ---------------------------------------------------------------------------
+  int role = tid % R::LANES;
+  if (role >= R::R_END) role -= (R::LANES - R::R_END);  // spare lanes duplicate a column (same value, same address)
+  const bool front = (tid % R::LANES) / 32 * 32 < R::FRONT;  // warp-uniform: this warp holds obs/stage/history roles
+  const int env_first = (tid / R::LANES) * EP;     // first env (within the tile) of this lane's part
+  const float* src;             // source of (env_first, column)
+  int stride;                   // source row stride in floats
+  int dcol;                     // output column (scaled): states[:, dcol], obs[:, dcol] if dcol < OBS; -1: none
+  float* stage = nullptr;       // shared destination of env_first's raw value, or null
+  int stage_stride = 0;
+  int hist_col = -1;            // column of the NEXT history entry this lane provides, or -1
+  {
+    const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
+    auto tip_src = [&](int tip, int c) {
+      const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
+      return S.rigid_body + body * 13 + c;
+    };
+    if (role < 18) {                                         // dof_state (pos, vel) interleaved  trifinger_env.py:1003-1007
+      src = S.dof_state + role; stride = 18;
+      dcol = (role & 1) * 9 + (role >> 1);
+    } else if (role < 25) {                                  // object pose (root row of actor 4e+2)  :975, :1011
+      const int c = role - 18;
+      src = S.root_state + P.object_slot * 13 + c; stride = actor_stride;
+      dcol = L::OFF_OBJ + c;
+      stage = s_obj + c; stage_stride = 7; hist_col = 9 + c;
+    } else if (role < 32) {                                  // goal pose buffer                  :1015
+      const int c = role - 25;
+      src = B.goal_pose + c; stride = 7;
+      dcol = L::OFF_GOAL + c;
+      stage = s_goal + c; stage_stride = 7;
+    } else if (role < R::OBS) {                              // last action                       :1019
+      const int c = role - 32;
+      src = B.action + c; stride = A;
+      dcol = L::OFF_ACT + c;
+    } else if (role < R::R_TIPREST) {                        // fingertip positions (bodies 6/11/16)  :974, :1040
+      const int j = role - R::R_TIPPOS, tip = j / 3, c = j - tip * 3;
+      src = tip_src(tip, c); stride = body_stride;
+      dcol = ASYM ? L::OFF_TIPS + tip * 13 + c : -1;
+      stage = s_tips + j; stage_stride = 9; hist_col = j;
+    } else if (role < R::R_OBJVEL) {                         // fingertip orientation + velocity
+      const int j = role - R::R_TIPREST, tip = j / 10, c = 3 + (j - tip * 10);
+      src = tip_src(tip, c); stride = body_stride;
+      dcol = L::OFF_TIPS + tip * 13 + c;
+    } else if (role < R::R_FT) {                             // object velocity                   :1035
+      const int c = role - R::R_OBJVEL;
+      src = S.root_state + P.object_slot * 13 + 7 + c; stride = actor_stride;
+      dcol = L::OFF_OBJVEL + c;
+    } else if (role < R::R_TQ) {                             // fingertip wrenches                :1051
+      const int c = role - R::R_FT;
+      src = S.ft_sensors + c; stride = 18;
+      dcol = L::OFF_FT + c;
+    } else {                                                 // dof torque                        :1047
+      const int c = role - R::R_TQ;
+      src = S.dof_force + c; stride = 9;
+      dcol = L::OFF_TORQUE + c;
+    }
+  }
+  src += (e0 + env_first) * stride;
+  pdl_wait();  // everything above is independent of the previous kernel's results
+  const int cnt = max(0, min(EP, nvalid - env_first));   // envs of this lane: env_first .. env_first + cnt - 1
+  const bool full = nvalid == E;                           // every CTA but possibly the last
+
+  // ---- phase 1: every global load of the tile in flight -----------------------------------------
+  float v[EP];
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < EP; ++k) v[k] = ld_stream1(src + (int64_t)k * stride);
+  } else {
+#pragma unroll
+    for (int k = 0; k < EP; ++k) v[k] = k < cnt ? ld_stream1(src + (int64_t)k * stride) : 0.0f;
+  }
+  // reward warps: thread (w, env) = (tid / 32, tid % 32), w < 4.  Each fetches one 16-byte piece of the
+  // env's previous history entry (64-byte rows), warp 0 also the env's flags and step counter.
+  const int rw = tid >> 5, renv = tid & 31;
+  const bool rlive = REWARD && rw < 4 && renv < nvalid;
+  float4 hprev = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint8_t in_goal_reset = 0, in_succ = 0, in_reset = 0;
+  int64_t in_steps = 0;
+  if (rlive) {
+    hprev = ld_stream4(reinterpret_cast<const float4*>(B.history + (e0 + renv) * LG_HISTORY_COLS) + rw);
+    if (rw == 0) {
+      const int64_t e = e0 + renv;
+      in_goal_reset = B.goal_reset[e]; in_succ = B.successes[e]; in_reset = B.reset[e]; in_steps = B.steps_count[e];
+    }
+  }
+  // this lane's scale_transform constants (torch_utils.py:33-36) in half-span form:
+  // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
+  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
+  if (P.normalize_obs && dcol >= 0) {
+    centre = __ldg(B.scale_table + dcol);
+    half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
+    rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
+  }
+
+  pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
+
+  // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----
+  if (tid < C_COUNT) s_coef[tid] = (REWARD && P.use_device_clock) ? __ldg(B.reward_coef + tid) : CF.v[tid];
+
+  // ---- phase 2: stage what the reward terms read, then ONE barrier -------------------------------
+  // Only the warps that hold staged columns wait for (a small part of) their data here; the others
+  // reach the barrier right after issuing their loads.  The reward math then runs on warps 0-3 while
+  // the bulk of the tile is still arriving and being scaled and stored by warps 4-7.
+  if (rlive) {
+    float* h = s_hist + renv * HS + rw * 4;
+    h[0] = hprev.x; h[1] = hprev.y; h[2] = hprev.z; h[3] = hprev.w;
+  }
+  // extension (DR observation noise): the tile's standard normals, generated by ALL threads while the loads are in
+  // flight — one Philox block + two Box-Muller pairs per (column, group of 4 envs by GLOBAL index), so the stream
+  // does not depend on tiling or sharding.  Columns with sigma = 0 are skipped.
+  if (EXT && P.dr_activate) {
+    const uint64_t base = (uint64_t)(P.env_offset + e0);
+    const uint64_t g0 = base >> 2;
+    const int ngroups = (int)(((base + E - 1) >> 2) - g0) + 1;
+    const uint32_t noise_epoch = __float_as_uint((REWARD && P.use_device_clock) ? __ldg(B.reward_coef + C_NOISE_EPOCH)
+                                                                                  : CF.v[C_NOISE_EPOCH]);
+    for (int i = tid; i < L::OBS * ngroups; i += kPostThreads) {
+      const int col = i / ngroups, g = i - col * ngroups;
+      if (__ldg(B.scale_table + 3 * LG_MAX_STATE_DIM + col) != 0.0f) {
+        const uint64_t grp = g0 + g;
+        const U4 r = philox4x32_10(U4{(uint32_t)grp, (uint32_t)(grp >> 32) ^ kPurposeNoise, (uint32_t)col, noise_epoch},
+                                   (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        float n[4];
+        box_muller(r.x, r.y, n[0], n[1]);
+        box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int64_t local = (int64_t)(4 * grp + q) - (int64_t)base;
+          if (local >= 0 && local < E) s_noise[col][local] = n[q];
+        }
+      }
+    }
+  }
+  if (front && stage) {
+    float* dst = stage + env_first * stage_stride;
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < EP; ++k) dst[k * stage_stride] = v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (k < cnt) dst[k * stage_stride] = v[k];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3 (all warps; the reward warps come back to it after their math) -------------------------
+  auto emit_outputs = [&](auto full_c) {
+    constexpr bool FULLC = decltype(full_c)::value;  // full tile: no per-element bound checks at all
+    // history shift (deque.appendleft, trifinger_env.py:974-975): current -> entry read next step.
+    // After the barrier: every read of the previous entry has completed.
+    if (front && hist_col >= 0) {
+      float* dst = B.history + (e0 + env_first) * LG_HISTORY_COLS + hist_col;
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (FULLC || k < cnt) dst[k * LG_HISTORY_COLS] = v[k];
+    }
+    float amax = 0.0f;  // largest numerator seen: beyond 2^100 (never, for physical data) the column is redone exactly
+    const float clip = P.clip_obs;
+    const int st_off = env_first * L::STATE + dcol, ob_off = env_first * L::OBS + dcol;
+    float* st = ASYM ? B.states + e0 * L::STATE + st_off : nullptr;                          // trifinger_env.py:990-994
+    float* stc = (CLIP && ASYM) ? B.states_clipped + e0 * L::STATE + st_off : nullptr;       // vec_task.py:147
+    const bool to_obs = front && dcol >= 0 && dcol < L::OBS;
+    float* ob = B.obs + e0 * L::OBS + ob_off;                                                // trifinger_env.py:983-987
+    float* obc = CLIP ? B.obs_clipped + e0 * L::OBS + ob_off : nullptr;                      // vec_task.py:167
+    // extension (no reference code; the TODO at trifinger_env.py:979): additive Gaussian noise on the RAW
+    // actor observation, before scale_transform; the critic's states stay clean.  sigma = 0 -> skipped.
+    const float sigma = (EXT && P.dr_activate && to_obs) ? __ldg(B.scale_table + 3 * LG_MAX_STATE_DIM + dcol) : 0.0f;
+    const bool noisy = EXT && __any_sync(0xffffffffu, sigma != 0.0f);
+    // optional bf16 copies for the policy / value networks: of the clipped values when the
+    // wrapper's clamp is fused in, else of the scaled values
+    uint16_t* stb = (EXT && ASYM && B.states_bf16) ? B.states_bf16 + e0 * L::STATE + st_off : nullptr;
+    uint16_t* obb = (EXT && B.obs_bf16) ? B.obs_bf16 + e0 * L::OBS + ob_off : nullptr;
+    // outputs go out with streaming stores (st.global.cs): nothing on the device reads them again before the
+    // learner does, and evict-first keeps them from displacing the simulator rows in L2 (measured: 84.0 -> 80.3 us
+    // at 262 144 envs, 7.25 -> 7.15 us at 16 384)
+#pragma unroll
+    for (int k = 0; k < EP; ++k) {
+      const float sv = div_by_const(v[k] - centre, half_span, rcp_half, amax);
+      if (FULLC || k < cnt) {
+        if (ASYM) {
+          __stcs(st + k * L::STATE, sv);
+          const float svc = CLIP ? fminf(fmaxf(sv, -clip), clip) : sv;
+          if (CLIP) __stcs(stc + k * L::STATE, svc);
+          if (EXT && stb) __stcs(stb + k * L::STATE, to_bf16(svc));
+        }
+        if (to_obs) {
+          float ov = sv;
+          if (noisy) {
+            const float n0 = s_noise[dcol][env_first + k];   // generated before the barrier, see above
+            ov = div_by_const((v[k] + sigma * n0) - centre, half_span, rcp_half, amax);
+          }
+          __stcs(ob + k * L::OBS, ov);
+          const float ovc = CLIP ? fminf(fmaxf(ov, -clip), clip) : ov;
+          if (CLIP) __stcs(obc + k * L::OBS, ovc);
+          if (EXT && obb) __stcs(obb + k * L::OBS, to_bf16(ovc));
+        }
+      }
+    }
+    if (dcol >= 0 && !(amax < kDivSafeMax))  // cold: same addresses, same thread: plain overwrite
+      output_exact<L::STATE, L::OBS, ASYM>(P, B, src, stride, cnt, e0 + env_first, dcol);
+    // moving goal (__update_goal_movement_post, trifinger_env.py:1279-1284): after the rewards, the goal pose
+    // buffer takes the pose the simulator integrated for the goal body.  The goal-role lanes own their elements
+    // of goal_pose (read above, overwritten here), so no other lane observes the change within this step.
+    if (EXT && REWARD && P.goal_rotation && front && role >= 25 && role < 32) {
+      const int c = role - 25, actor_stride = P.actors_per_env * 13;
+      const float* g_src = S.root_state + ((e0 + env_first) * P.actors_per_env + P.goal_slot) * 13 + c;
+      float* g_dst = B.goal_pose + (e0 + env_first) * 7 + c;
+#pragma unroll
+      for (int k = 0; k < EP; ++k)
+        if (FULLC || k < cnt) g_dst[k * 7] = g_src[(int64_t)k * actor_stride];
+    }
+  };
+  // ======== reward warps: lane = env, warp = sub-task (uniform control flow inside a warp) ================
+  if (REWARD && rw < 4) {
+    const int env = renv;
+    const bool live = renv < nvalid;
+    const float* obj = s_obj + env * 7;
+    const float* goal = s_goal + env * 7;
+    const float* tips = s_tips + env * 9;
+    const float* hist = s_hist + env * HS;
+    if (live) {
+      const float gx = goal[0], gy = goal[1], gz = goal[2];
+      if (rw == 0) {
+        // finger_reach_object_rate (rewards.py:219-235): sum_i (|tip_i - obj| - |tip_i' - obj'|)
+        const float ox = obj[0], oy = obj[1], oz = obj[2];
+        const float px = hist[9], py = hist[10], pz = hist[11];
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float cur = norm3(tips[3 * i] - ox, tips[3 * i + 1] - oy, tips[3 * i + 2] - oz);
+          const float prev = norm3(hist[3 * i] - px, hist[3 * i + 1] - py, hist[3 * i + 2] - pz);
+          acc = acc + (cur - prev);
+        }
+        s_part[0][env] = s_coef[C_REACH] * acc;
+      } else if (rw == 1) {
+        // finger_move_penalty (rewards.py:261-263): sum_9 ((tip - tip') / dt)^2
+        const float dt = s_coef[C_DT], dt_rcp = s_coef[C_DT_RCP];
+        float acc = 0.0f, dmax = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float d = div_by_const(tips[k] - hist[k], dt, dt_rcp, dmax);
+          acc = acc + d * d;
+        }
+        if (!(dmax < kDivSafeMax)) {  // cold
+          acc = 0.0f;
+          for (int k = 0; k < 9; ++k) {
+            const float d = __fdiv_rn(tips[k] - hist[k], dt);
+            acc = acc + d * d;
+          }
+        }
+        s_part[1][env] = s_coef[C_MOVE] * acc;
+        // object_dist (rewards.py:62-63) and object_move (rewards.py:88-91)
+        const float d = norm3(obj[0] - gx, obj[1] - gy, obj[2] - gz);
+        const float dprev = norm3(hist[9] - gx, hist[10] - gy, hist[11] - gz);
+        s_part[2][env] = lgsk(d, 50.0f) * s_coef[C_DIST];
+        s_part[3][env] = s_coef[C_OBJMOVE] * (d - dprev);
+        s_part[4][env] = d;
+      } else {
+        const Quat gq{goal[3], goal[4], goal[5], goal[6]};
+        if (rw == 2) {
+          // object_rot (rewards.py:134-139): w * (gate*dt) / (scale*|theta| + scale)
+          const Quat oq{obj[3], obj[4], obj[5], obj[6]};
+          const float theta = quat_diff_rad(oq, gq);
+          const float den = s_coef[C_ROT_SCALE] * fabsf(theta) + s_coef[C_ROT_SCALE];
+          s_part[5][env] = (__frcp_rn(den) * s_coef[C_ROT_SCHED]) * s_coef[C_ROT_W];
+          s_part[6][env] = theta;
+        } else {
+          // previous-orientation angle for object_rot_delta (rewards.py:179)
+          const Quat pq{hist[12], hist[13], hist[14], hist[15]};
+          s_part[7][env] = fabsf(quat_diff_rad(pq, gq));
+        }
+      }
+      // extension (no reference code): keypoint pose reward
+      //   w dt mean_k lgsk(|kp_k - kp_k^goal|; scale, eps), kp_k = p + R(q) c_k over the 8 cube corners;
+      // two corners per reward warp, summed by warp 0
+      if (EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1)) {
+        const Quat oq{obj[3], obj[4], obj[5], obj[6]};
+        const Quat gq{goal[3], goal[4], goal[5], goal[6]};
+        const float h = (float)P.cube_half_size;
+        float acc = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int kk = 2 * rw + q;
+          const float cx = (kk & 1) ? h : -h, cy = (kk & 2) ? h : -h, cz = (kk & 4) ? h : -h;
+          float ax, ay, az, bx, by, bz;
+          quat_rotate(oq, cx, cy, cz, ax, ay, az);
+          quat_rotate(gq, cx, cy, cz, bx, by, bz);
+          const float dd = norm3((obj[0] + ax) - (gx + bx), (obj[1] + ay) - (gy + by), (obj[2] + az) - (gz + bz));
+          acc = acc + lgsk(dd, s_coef[C_KP_SCALE], s_coef[C_KP_EPS]);
+        }
+        s_part[8 + rw][env] = acc;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four reward warps
+  }
+  if (REWARD && rw == 0) {
+    // ---- warp 0: combine, terminate, count (one lane per env) -----------------------------------------
+    const int env = renv;
+    const bool live = renv < nvalid;
+    float st[LG_NUM_STATS];
+#pragma unroll
+    for (int i = 0; i < LG_NUM_STATS; ++i) st[i] = 0.0f;
+    if (live) {
+      const int64_t e = e0 + env;
+      const float dist = s_part[4][env], theta = s_part[6][env];
+      // object_rot_delta (rewards.py:180-184): w * (ramp * (|theta| - |theta'|))
+      const float t_delta = s_coef[C_DELTA_W] * (s_coef[C_DELTA_RAMP] * (fabsf(theta) - s_part[7][env]));
+      const bool kp_on = EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1);
+      const float terms[7] = {s_part[0][env], s_part[1][env], s_part[2][env], s_part[5][env], t_delta, s_part[3][env],
+                              kp_on ? s_coef[C_KP_W] * ((((s_part[8][env] + s_part[9][env]) + s_part[10][env]) + s_part[11][env]) * 0.125f)
+                                    : 0.0f};
+      float reward = 0.0f;  // trifinger_env.py:511, :551-553 — accumulation in dict order (the extension term last)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        if ((P.term_active_mask >> k) & 1) { reward = reward + terms[k]; st[LG_STAT_TERM0 + k] = terms[k]; }
+        if (B.term_rewards) B.term_rewards[(int64_t)k * P.num_envs + e] = terms[k];
+      }
+      // __check_termination (trifinger_env.py:1053-1099)
+      const bool pos_ok = dist <= s_coef[C_POS_TOL];
+      const bool rot_ok = theta <= s_coef[C_ROT_TOL];
+      bool done;
+      if (P.task_difficulty < 4) done = pos_ok;
+      else if (P.task_difficulty == 4) done = pos_ok && rot_ok;
+      else done = rot_ok;
+      bool goal_reset = in_goal_reset != 0;
+      bool succ = in_succ != 0;
+      if (P.success_activate) {
+        if (done) reward = reward + s_coef[C_BONUS];
+        goal_reset = done;
+        succ = succ || goal_reset;
+        B.goal_reset[e] = goal_reset;
+      } else {
+        succ = goal_reset && succ;
+      }
+      B.successes[e] = succ;
+      B.reward[e] = reward;
+      // step counter, timeout, dones (envs/env_base.py:391-399)
+      bool reset = in_reset != 0;
+      if (P.fuse_bookkeeping) {
+        const int64_t steps = in_steps + 1;
+        B.steps_count[e] = steps;
+        if (P.episode_length >= 0) reset = reset || (steps >= P.episode_length);
+        B.reset[e] = reset;
+      }
+      const bool dn = reset && goal_reset;
+      if (B.dones) B.dones[e] = dn;
+      st[LG_STAT_POSITION_GOAL] = pos_ok;
+      st[LG_STAT_ORIENTATION_GOAL] = rot_ok;
+      st[LG_STAT_SUCCESSES] = succ;
+      st[LG_STAT_REWARD] = reward;
+      st[LG_STAT_RESETS] = reset;
+      st[LG_STAT_DONES] = dn;
+    }
+    // ---- episode statistics: per-CTA fp64 sums in a fixed order, one RED per slot, no fence ----------
+    if (env < E) {  // lanes beyond the tile hold nothing (E < 32)
+#pragma unroll
+      for (int i = 0; i <= LG_STAT_DONES; ++i) s_stat[i][env] = st[i];
+    }
+    __syncwarp();
+    if (env <= LG_STAT_DONES) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four chains: the fp64 adds are dependent otherwise
+#pragma unroll
+      for (int k = 0; k < E; k += 4) {
+        a0 += (double)s_stat[env][k];
+        a1 += (double)s_stat[env][k + 1];
+        a2 += (double)s_stat[env][k + 2];
+        a3 += (double)s_stat[env][k + 3];
+      }
+      double acc = (a0 + a1) + (a2 + a3);
+      // reward-term, reward and success entries are means over this shard (trifinger_env.py:554, :1098),
+      // the rest are counts (:1067, :1076)
+      const bool is_mean = env < LG_STAT_POSITION_GOAL || env == LG_STAT_SUCCESSES || env == LG_STAT_REWARD;  // 0..6: terms
+      if (is_mean) acc = acc / (double)(P.stats_num_envs > 0 ? P.stats_num_envs : P.num_envs);
+      atomicAdd(B.step_stats + env, acc);
+    }
+  }
+  if (full) emit_outputs(std::true_type{});
+  else emit_outputs(std::false_type{});
+}
+
+// history seeding (trifinger_env.py:619-628): both entries = initial simulator state
+__global__ void init_history_kernel(const __grid_constant__ LgParams P, const LgSimState S, const LgBuffers B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.num_envs * LG_HISTORY_COLS) return;
+  const int64_t e = i >> 4;
+  const int c = (int)(i & 15);
+  float v;
+  if (c < 9) v = S.rigid_body[(e * P.bodies_per_env + P.fingertip_body[c / 3]) * 13 + (c % 3)];
+  else v = S.root_state[((int64_t)P.actors_per_env * e + P.object_slot) * 13 + (c - 9)];
+  B.history[i] = v;
+}
+
+}  // namespace lg
