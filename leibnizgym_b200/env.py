@@ -163,7 +163,10 @@ class IsaacEnvBase:
         if getattr(self, "_host_io", False) and action.device.type == "cpu" and action.is_pinned() \
                 and action.dtype == torch.float and action.is_contiguous():
             return action  # pinned host memory is addressable from the kernel (UVA): no staging copy
-        return action.to(self._torch_device, dtype=torch.float, non_blocking=True).contiguous()
+        action = action.to(self._torch_device, dtype=torch.float, non_blocking=True).contiguous()
+        if action.data_ptr() % 16:   # an offset view (e.g. a slice of a larger rollout buffer): the bulk copies need 16 B
+            action = action.clone()
+        return action
 
     def step(self, action: Union[np.ndarray, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         """Generic hook-by-hook sequencing (ref env_base.py:345-401); TrifingerEnv overrides it

@@ -482,3 +482,27 @@ def _angle_allowance_small(ora):
     terms = np.zeros((6, len(cur)))
     terms[3], terms[4] = rot, delta
     return terms, rot * t["object_rot"]["activate"] + delta * t["object_rot_delta"]["activate"]
+
+
+def test_misaligned_action_views_are_accepted():
+    """An action that is an offset view of a bigger buffer (not 16-byte aligned) steps like its aligned copy."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    N = 640
+    seq = make_sequence(2, 3, N)
+    cfg = difficulty_config(2, N, seed=1)
+    a = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    b = TrifingerEnv(cfg, device="cuda:0", verbose=False, sim=SyntheticSim(seq.to("cuda:0"), "cuda:0"))
+    a.reset()
+    b.reset()
+    big = torch.zeros(N * 9 + 1, device="cuda:0")
+    view = big[1:].view(N, 9)
+    view.copy_(seq.action[1])
+    assert view.data_ptr() % 16 != 0
+    oa = a.step(seq.action[1].cuda())
+    ob = b.step(view)
+    for x, y in zip(oa[:3], ob[:3]):
+        assert torch.equal(x, y)
+    assert torch.equal(a.action_buf, b.action_buf)
