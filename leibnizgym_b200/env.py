@@ -78,6 +78,30 @@ class IsaacEnvBase:
         self._steps_count_buf = torch.zeros(N, device=dev, dtype=torch.long)
 
     # -- getters (ref env_base.py:222-255) ---------------------------------------------
+    # -- simulator control plane (ref env_base.py:175-220): owned by the simulator object, forwarded when it has them
+    def _sim_call(self, name: str, *args):
+        fn = getattr(getattr(self, "_sim", None), name, None)
+        if fn is None:
+            raise NotImplementedError(f"the simulator object does not provide `{name}` (physics is out of this package's scope)")
+        return fn(*args)
+
+    def set_gravity(self, gravity=(0, 0, -9.81)):
+        self.config["sim"]["gravity"] = [float(g) for g in gravity]
+        if hasattr(getattr(self, "_sim", None), "set_gravity"):
+            self._sim.set_gravity(gravity)
+
+    def get_gravity(self) -> np.ndarray:
+        return np.asarray(self.config["sim"]["gravity"], dtype=np.float64)
+
+    def set_sim_params(self, params):
+        return self._sim_call("set_sim_params", params)
+
+    def get_sim_params(self):
+        return self._sim_call("get_sim_params")
+
+    def set_camera_lookat(self, pos, target):
+        return self._sim_call("set_camera_lookat", pos, target)
+
     def get_state_shape(self) -> torch.Size:
         return self._states_buf.size()
 
