@@ -142,7 +142,101 @@ struct Roles {
   static_assert(R_END <= LANES, "more output columns than role lanes");
 };
 
-template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT>
+// What a role lane needs to know, independent of the tile: where its column comes from, where it goes, and whether
+// the raw value is staged for the reward math / kept as next step's history.
+struct RoleInfo {
+  int src_id;        // 0 dof_state, 1 root_state, 2 goal_pose, 3 action, 4 rigid_body, 5 ft_sensors, 6 dof_force
+  int src_off;       // float offset of (env 0, column) inside that tensor
+  int stride;        // source row stride in floats
+  int dcol;          // output column (scaled): states[:, dcol], obs[:, dcol] if dcol < OBS; -1: none
+  int stage_id;      // 0 none, 1 object pose, 2 goal pose, 3 fingertip positions
+  int stage_off;     // column inside that staging array
+  int stage_stride;  // staging row stride
+  int hist_col;      // column of the NEXT history entry this lane provides, or -1
+};
+
+template <int A, bool ASYM>
+__device__ __forceinline__ RoleInfo role_info(const LgParams& P, int role) {
+  using L = Layout<A, ASYM>;
+  using R = Roles<A, ASYM, 32>;   // the role ranges do not depend on the tile size
+  RoleInfo r;
+  r.stage_id = 0; r.stage_off = 0; r.stage_stride = 0; r.hist_col = -1;
+  const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
+  auto tip_off = [&](int tip, int c) {
+    const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
+    return body * 13 + c;
+  };
+  if (role < 18) {                                         // dof_state (pos, vel) interleaved  trifinger_env.py:1003-1007
+    r.src_id = 0; r.src_off = role; r.stride = 18;
+    r.dcol = (role & 1) * 9 + (role >> 1);
+  } else if (role < 25) {                                  // object pose (root row of actor 4e+2)  :975, :1011
+    const int c = role - 18;
+    r.src_id = 1; r.src_off = P.object_slot * 13 + c; r.stride = actor_stride;
+    r.dcol = L::OFF_OBJ + c;
+    r.stage_id = 1; r.stage_off = c; r.stage_stride = 7; r.hist_col = 9 + c;
+  } else if (role < 32) {                                  // goal pose buffer                  :1015
+    const int c = role - 25;
+    r.src_id = 2; r.src_off = c; r.stride = 7;
+    r.dcol = L::OFF_GOAL + c;
+    r.stage_id = 2; r.stage_off = c; r.stage_stride = 7;
+  } else if (role < R::OBS) {                              // last action                       :1019
+    const int c = role - 32;
+    r.src_id = 3; r.src_off = c; r.stride = A;
+    r.dcol = L::OFF_ACT + c;
+  } else if (role < R::R_TIPREST) {                        // fingertip positions (bodies 6/11/16)  :974, :1040
+    const int j = role - R::R_TIPPOS, tip = j / 3, c = j - tip * 3;
+    r.src_id = 4; r.src_off = tip_off(tip, c); r.stride = body_stride;
+    r.dcol = ASYM ? L::OFF_TIPS + tip * 13 + c : -1;
+    r.stage_id = 3; r.stage_off = j; r.stage_stride = 9; r.hist_col = j;
+  } else if (role < R::R_OBJVEL) {                         // fingertip orientation + velocity
+    const int j = role - R::R_TIPREST, tip = j / 10, c = 3 + (j - tip * 10);
+    r.src_id = 4; r.src_off = tip_off(tip, c); r.stride = body_stride;
+    r.dcol = L::OFF_TIPS + tip * 13 + c;
+  } else if (role < R::R_FT) {                             // object velocity                   :1035
+    const int c = role - R::R_OBJVEL;
+    r.src_id = 1; r.src_off = P.object_slot * 13 + 7 + c; r.stride = actor_stride;
+    r.dcol = L::OFF_OBJVEL + c;
+  } else if (role < R::R_TQ) {                             // fingertip wrenches                :1051
+    const int c = role - R::R_FT;
+    r.src_id = 5; r.src_off = c; r.stride = 18;
+    r.dcol = L::OFF_FT + c;
+  } else {                                                 // dof torque                        :1047
+    const int c = role - R::R_TQ;
+    r.src_id = 6; r.src_off = c; r.stride = 9;
+    r.dcol = L::OFF_TORQUE + c;
+  }
+  return r;
+}
+
+// The role set-up is ~150 instructions of branches per thread — a sixth of the kernel — and depends on nothing but
+// the simulator layout.  lg_build_role_table evaluates it once per env object into a 32-byte entry per role lane
+// (this kernel), and the TABLE instantiation of the post-physics kernel reads its entry with two 16-byte loads that
+// sit before the dependency wait.  Entry: int4 {src_id | stage_id<<4 | stage_stride<<8 | (hist_col+1)<<16, src_off,
+// stride, dcol}, float4 {centre, span/2, 2/span, stage_off (bits)}.
+constexpr int kRoleEntryFloats = 8;
+template <int A, bool ASYM>
+__global__ void build_role_table_kernel(const __grid_constant__ LgParams P, const float* __restrict__ scale_table,
+                                        float* __restrict__ table) {
+  using R = Roles<A, ASYM, 32>;
+  const int lane = threadIdx.x;
+  if (lane >= R::LANES) return;
+  int role = lane;
+  if (role >= R::R_END) role -= (R::LANES - R::R_END);
+  const RoleInfo r = role_info<A, ASYM>(P, role);
+  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
+  if (P.normalize_obs && r.dcol >= 0) {
+    centre = scale_table[r.dcol];
+    half_span = 0.5f * scale_table[LG_MAX_STATE_DIM + r.dcol];
+    rcp_half = 2.0f * scale_table[2 * LG_MAX_STATE_DIM + r.dcol];
+  }
+  int4 a;
+  a.x = r.src_id | (r.stage_id << 4) | (r.stage_stride << 8) | ((r.hist_col + 1) << 16);
+  a.y = r.src_off; a.z = r.stride; a.w = r.dcol;
+  reinterpret_cast<int4*>(table)[2 * lane] = a;
+  reinterpret_cast<float4*>(table)[2 * lane + 1] = make_float4(centre, half_span, rcp_half, __int_as_float(r.stage_off));
+}
+
+template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT, bool TABLE>
 __global__ void __launch_bounds__(kPostThreads, 4)
 post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                     const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
@@ -175,51 +269,26 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   float* stage = nullptr;       // shared destination of env_first's raw value, or null
   int stage_stride = 0;
   int hist_col = -1;            // column of the NEXT history entry this lane provides, or -1
+  // this lane's scale_transform constants (torch_utils.py:33-36) in half-span form:
+  // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
+  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
   {
-    const int body_stride = P.bodies_per_env * 13, actor_stride = P.actors_per_env * 13;
-    auto tip_src = [&](int tip, int c) {
-      const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
-      return S.rigid_body + body * 13 + c;
-    };
-    if (role < 18) {                                         // dof_state (pos, vel) interleaved  trifinger_env.py:1003-1007
-      src = S.dof_state + role; stride = 18;
-      dcol = (role & 1) * 9 + (role >> 1);
-    } else if (role < 25) {                                  // object pose (root row of actor 4e+2)  :975, :1011
-      const int c = role - 18;
-      src = S.root_state + P.object_slot * 13 + c; stride = actor_stride;
-      dcol = L::OFF_OBJ + c;
-      stage = s_obj + c; stage_stride = 7; hist_col = 9 + c;
-    } else if (role < 32) {                                  // goal pose buffer                  :1015
-      const int c = role - 25;
-      src = B.goal_pose + c; stride = 7;
-      dcol = L::OFF_GOAL + c;
-      stage = s_goal + c; stage_stride = 7;
-    } else if (role < R::OBS) {                              // last action                       :1019
-      const int c = role - 32;
-      src = B.action + c; stride = A;
-      dcol = L::OFF_ACT + c;
-    } else if (role < R::R_TIPREST) {                        // fingertip positions (bodies 6/11/16)  :974, :1040
-      const int j = role - R::R_TIPPOS, tip = j / 3, c = j - tip * 3;
-      src = tip_src(tip, c); stride = body_stride;
-      dcol = ASYM ? L::OFF_TIPS + tip * 13 + c : -1;
-      stage = s_tips + j; stage_stride = 9; hist_col = j;
-    } else if (role < R::R_OBJVEL) {                         // fingertip orientation + velocity
-      const int j = role - R::R_TIPREST, tip = j / 10, c = 3 + (j - tip * 10);
-      src = tip_src(tip, c); stride = body_stride;
-      dcol = L::OFF_TIPS + tip * 13 + c;
-    } else if (role < R::R_FT) {                             // object velocity                   :1035
-      const int c = role - R::R_OBJVEL;
-      src = S.root_state + P.object_slot * 13 + 7 + c; stride = actor_stride;
-      dcol = L::OFF_OBJVEL + c;
-    } else if (role < R::R_TQ) {                             // fingertip wrenches                :1051
-      const int c = role - R::R_FT;
-      src = S.ft_sensors + c; stride = 18;
-      dcol = L::OFF_FT + c;
-    } else {                                                 // dof torque                        :1047
-      const int c = role - R::R_TQ;
-      src = S.dof_force + c; stride = 9;
-      dcol = L::OFF_TORQUE + c;
+    int src_id, src_off, stage_id, stage_off;
+    if constexpr (TABLE) {
+      const int4 a = __ldg(reinterpret_cast<const int4*>(B.role_table) + 2 * (tid % R::LANES));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B.role_table) + 2 * (tid % R::LANES) + 1);
+      src_id = a.x & 15; stage_id = (a.x >> 4) & 15; stage_stride = (a.x >> 8) & 255; hist_col = ((a.x >> 16) & 255) - 1;
+      src_off = a.y; stride = a.z; dcol = a.w;
+      centre = b.x; half_span = b.y; rcp_half = b.z; stage_off = __float_as_int(b.w);
+    } else {
+      const RoleInfo r = role_info<A, ASYM>(P, role);
+      src_id = r.src_id; src_off = r.src_off; stride = r.stride; dcol = r.dcol;
+      stage_id = r.stage_id; stage_off = r.stage_off; stage_stride = r.stage_stride; hist_col = r.hist_col;
     }
+    const float* base = src_id == 0 ? S.dof_state : src_id == 1 ? S.root_state : src_id == 2 ? B.goal_pose
+                      : src_id == 3 ? B.action : src_id == 4 ? S.rigid_body : src_id == 5 ? S.ft_sensors : S.dof_force;
+    src = base + src_off;
+    if (stage_id) stage = (stage_id == 1 ? s_obj : stage_id == 2 ? s_goal : s_tips) + stage_off;
   }
   src += (e0 + env_first) * stride;
   pdl_wait();  // everything above is independent of the previous kernel's results
@@ -249,10 +318,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       in_goal_reset = B.goal_reset[e]; in_succ = B.successes[e]; in_reset = B.reset[e]; in_steps = B.steps_count[e];
     }
   }
-  // this lane's scale_transform constants (torch_utils.py:33-36) in half-span form:
-  // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
-  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
-  if (P.normalize_obs && dcol >= 0) {
+  if (!TABLE && P.normalize_obs && dcol >= 0) {
     centre = __ldg(B.scale_table + dcol);
     half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
     rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
