@@ -334,14 +334,26 @@ def run_gpu(args, wl):
             main_graph.replay()
         barrier()
         # ---- timed region: exactly K steps -----------------------------------------------------
+        # Episode statistics are the path's only collective: every 512 steps the 16 shard sums are
+        # snapshotted on the step stream and all-reduced on a side stream, the way a logger consumes them — the
+        # steps do not wait for the other ranks; the timed region ends only when the last reduction has finished.
+        side = torch.cuda.Stream() if world > 1 else None
+        reduced = []
         e0, e1 = ev(), ev()
         e0.record()
         for i in range(q):
             main_graph.replay()
-            if world > 1 and (i % 4) == 3:   # episode statistics: the path's only collective
-                dist.all_reduce(env._step_stats.clone(), op=dist.ReduceOp.SUM)
+            if world > 1 and (i % 4) == 3:
+                snap = env._step_stats.clone()
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    dist.all_reduce(snap, op=dist.ReduceOp.SUM)
+                    snap.record_stream(side)
+                reduced.append(snap)
         if tail_graph is not None:
             tail_graph.replay()
+        if side is not None:
+            stream.wait_stream(side)
         e1.record()
         barrier()
         step_ms_total = e0.elapsed_time(e1)
