@@ -157,3 +157,24 @@ def test_simulator_control_plane_is_forwarded_or_refused():
     assert env.get_sim_params() == {"dt": 0.01}
     with pytest.raises(NotImplementedError):
         env.set_camera_lookat((1, 1, 1), (0, 0, 0))
+
+
+def test_every_bench_workload_resolves_to_kernel_parameters():
+    """bench.py's workloads (SURVEY.md 8d C2-C5 and their variants) produce valid env configs and parameter blocks,
+    with and without the extension features."""
+    import importlib.util
+    import os
+    from leibnizgym_b200.config import resolve_config
+    from leibnizgym_b200.params import build_params
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert {"c2", "c3", "c4", "c5"} <= set(bench.WORKLOADS)
+    for name, wl in bench.WORKLOADS.items():
+        for ext in (True, False):
+            cfg = resolve_config(bench.workload_config(wl, 256, extensions=ext))
+            P = build_params(cfg, 256)
+            assert P.num_envs == 256 and P.asymmetric_obs == int(wl["asym"]), name
+            assert bool(P.dr_activate) == bool(ext and wl.get("dr")), name
+            assert bool((P.term_active_mask >> 6) & 1) == bool(ext and wl.get("keypoint")), name
