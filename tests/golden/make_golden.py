@@ -247,7 +247,7 @@ def generate(name):
             raise SystemExit(f"{name}: scripted and eager runs disagree on {k}")
     for k, v in fe.items():  # draws exist only in the eager run
         fj.setdefault(k, v)
-    path = os.path.join(HERE, f"{name}.npz")
+    path = os.path.join(os.environ.get("LEIBNIZ_GOLDEN_OUT", HERE), f"{name}.npz")
     np.savez_compressed(path, **fj)
     print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB, {len(fj)} arrays")
 

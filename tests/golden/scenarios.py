@@ -85,3 +85,13 @@ SCENARIOS = {
                    config=_cfg(6, 20, False, 1009, normalize_action=False,
                                reset_distribution={"object_initial_state": {"type": "none"}})),
 }
+
+# Extra scenarios for the fuzzer (tests/golden/fuzz_reference.py): a JSON file of {name: scenario} named by the
+# environment, so that the generator's child processes see them too.  Never set by the test-suite.
+import json as _json   # noqa: E402
+import os as _os       # noqa: E402
+_extra = _os.environ.get("LEIBNIZ_EXTRA_SCENARIOS")
+if _extra and _os.path.exists(_extra):
+    with open(_extra) as _f:
+        SCENARIOS.update(_json.load(_f))
+

@@ -26,7 +26,7 @@ def golden_names():
 class Golden:
     def __init__(self, name: str):
         self.name = name
-        self.z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+        self.z = np.load(name if os.path.isabs(name) else os.path.join(GOLDEN_DIR, f"{name}.npz"))
         self.meta = json.loads(str(self.z["meta"]))
         self.N, self.T = self.meta["N"], self.meta["T"]
         self.config = self.meta["config"]
