@@ -25,7 +25,6 @@ Every function cites the reference lines it restates (paths relative to
 """
 from __future__ import annotations
 
-import math
 from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 

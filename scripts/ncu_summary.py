@@ -1,4 +1,4 @@
-import csv, sys, subprocess, collections
+import csv, sys, subprocess
 rep=sys.argv[1]
 raw=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
 rows=list(csv.reader(raw.splitlines()))

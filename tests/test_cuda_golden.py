@@ -1,6 +1,5 @@
 """GPU parity against the UNMODIFIED reference: every fixture of tests/golden is replayed
 through the CUDA TrifingerEnv (C ABI) with the reference's random draws injected."""
-import numpy as np
 import pytest
 
 from golden_io import Golden, golden_names, replay
