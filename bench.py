@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the TriFinger MDP hot path (reward + obs/states + reset), BASELINE.json metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--all-workloads] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
 
 A "step" is one pass of the hot path over all envs of the workload: lg_pre_physics (action store,
@@ -10,8 +10,10 @@ six reward terms, termination, counters, episode statistics).  PhysX is replaced
 synthetic simulator states resident in HBM (leibnizgym_b200/synthetic.py).
 
 One JSON line is printed by rank 0:
-  value      env-steps/s over all GPUs, inputs resident in HBM, K steps replayed from CUDA graphs,
-             timed with CUDA events, max over ranks
+  value      env-steps/s over all GPUs, inputs resident in HBM: the K-step region is replayed from CUDA
+             graphs until >= 50 ms of device time is covered, each repeat timed with CUDA events (max over
+             ranks) in steady state; value = K * envs / median region time (`timing` holds p10 / p90,
+             the repeat count and the cold-start figure)
   e2e        the same metric through the public API (VecTaskPython.step + get_state) with the
              simulator state and the action in pinned HOST memory and obs/states/reward/dones
              read back to the host every step
@@ -45,6 +47,11 @@ FALLBACK_HBM_GBS = 6650.0
 
 # BASELINE.json configs -> concrete runs.  envs are PER GPU (weak scaling).
 WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "c1": dict(desc="trifinger_difficulty_1, asymmetric obs+states, 1024 envs/GPU", difficulty=1, envs=1024, asym=True,
+               seed=1001, reset_p=0.0),
+    "c1sym": dict(desc="trifinger_difficulty_1, symmetric obs only, 1024 envs/GPU", difficulty=1, envs=1024, asym=False,
+                  seed=1001, reset_p=0.0),
     "c2": dict(desc="trifinger_difficulty_2, asymmetric obs+states, 16384 envs/GPU", difficulty=2, envs=16384,
                asym=True, seed=1002, reset_p=0.0),
     # DR noise (extension, no reference code) + goal resampling forced on 5 % of the envs per step
@@ -66,6 +73,9 @@ WORKLOADS = {
                   asym=False, seed=1002, reset_p=0.0),
 }
 
+# one line per BASELINE.json config for --all-workloads (c3 with the reference's features only; the DR-noise and
+# keypoint extensions have no reference implementation and stay out of every headline)
+ALL_WORKLOADS = ("c1", "c1sym", "c2", "c3ref", "c4", "c5")
 
 
 def workload_config(wl, num_envs, extensions=True):
@@ -148,16 +158,23 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
-    def __enter__(self):
-        if self.enabled:
+    def start(self):
+        if self.enabled and self._thread is None:
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
-        return self
 
-    def __exit__(self, *exc):
+    def stop(self):
         self._stop.set()
         if self._thread:
             self._thread.join()
+            self._thread = None
+
+    def __enter__(self):
+        self.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
 
     def summary(self):
         if not self.samples:
@@ -254,21 +271,51 @@ def time_cpu_path(wl: dict, envs: int, steps: int, warmup: int, max_seconds: flo
                 cores=torch.get_num_threads())
 
 
+def ring_slots(args, envs: int) -> int:
+    """Distinct simulator states (and output slots) resident in HBM: enough that one pass over the ring moves several
+    times the 126 MB L2, capped so that the largest workloads stay within a few GB."""
+    if args.ring:
+        return args.ring
+    per_slot = envs * (1724 + 616)          # bytes of simulator state + obs/states outputs per env and slot
+    return int(max(4, min(32, -(-(1280 << 20) // per_slot))))
+
+
+def make_config(wl: dict, world: int, ring: int, ring_mib: float) -> dict:
+    """The `config` object of the JSON line — the same dict from the B200 arm and from `--impl reference`."""
+    N = wl["envs"]
+    return {"workload": wl["desc"], "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"dp{world}",
+            "l2_policy": f"inputs larger than L2: ring of {ring} distinct simulator states ({ring_mib:.0f} MiB) and "
+                         f"{ring} output slots per GPU",
+            "reset_fraction_per_step": wl["reset_p"], "goal_reset_fraction_per_step": wl.get("goal_p", 0.0),
+            "extensions": [k for k in ("dr", "keypoint") if wl.get(k)]}
+
+
+def ring_mib_of(envs: int, ring: int) -> float:
+    return ring * envs * 1724 / 2**20   # 18+52+260+9+18+9 floats of simulator state and action per env and slot
+
+
 def run_reference(args, wl):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference tree does not
+    travel to the GPU box) on all host cores.  Same metric / unit / config as the B200 arm; every step is a bounded
+    sample of the workload (at most the workload's envs per GPU — at N > 1 the CPU arm still runs ONE shard's envs,
+    on rank 0 only; env-steps/s of a CPU path does not depend on how many GPUs the other arm uses)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     # bounded sample: each step covers a slice of the workload's envs so K steps end within ~1 min
     budget_env_steps = 4.0e7
     envs = int(min(wl["envs"], max(256, 2 ** int(math.log2(max(budget_env_steps / max(args.steps, 1), 256))))))
     r = time_cpu_path(wl, envs, args.steps, max(args.warmup, 3) if args.warmup < 16 else 16, max_seconds=150.0)
-    sample = (f"{r['steps']} steps x {envs} envs of the workload's {wl['envs']} per step, oracle port of the reference's "
-              f"torch CPU path, {r['cores']} torch threads, simulator playback excluded")
+    sample = (f"{r['steps']} steps x {envs} envs per step (one shard of the workload: {wl['envs']} envs per GPU; the CPU arm "
+              f"runs one shard at every N), oracle port of the reference's torch CPU path, {r['cores']} torch threads, "
+              f"simulator playback excluded")
+    R = ring_slots(args, wl["envs"])
     line = {
         "impl": "reference", "metric": METRIC, "value": r["env_steps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step_sampled": envs},
+        "config": make_config(wl, world, R, ring_mib_of(wl["envs"], R)),
         "cpu_baseline": {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["env_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -279,13 +326,183 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_gpu(args, wl):
+def pctl(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    i = (len(xs) - 1) * q
+    lo, hi = int(math.floor(i)), int(math.ceil(i))
+    return xs[lo] + (xs[hi] - xs[lo]) * (i - lo)
+
+
+class DeviceTimer:
+    """Steady-state timing of a replayed region with CUDA events, max over ranks.
+
+    One repeat = barrier + synchronize | one untimed lead-in replay | event | the K-step region (+ the statistics
+    all-reduce when sharded) | event | synchronize.  The lead-in keeps the GPU busy while the host enqueues the timed
+    replays, so the events bracket K steps of a running pipeline, not the launch latency of the first graph of an idle
+    stream (that figure is reported separately as `cold_start_ms_per_step`).  Repeats continue until `min_ms` of timed
+    device time is covered; the result is the median region time and p10 / p90."""
+
+    def __init__(self, world: int, dev: str):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def agree(self, x: float, op="max") -> float:
+        import torch.distributed as dist
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def once(self, region, lead_in=None) -> float:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        if lead_in is not None:
+            lead_in()
+        e0.record()
+        region()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def run(self, region, lead_in, min_ms: float = 50.0, min_rep: int = 7, max_rep: int = 400):
+        est = self.agree(self.once(region, lead_in))
+        reps = int(max(min_rep, min(max_rep, math.ceil(min_ms / max(est, 1e-3)))))
+        ms = [self.once(region, lead_in) for _ in range(reps)]
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor(ms, device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)      # per repeat: the slowest rank
+            ms = t.tolist()
+        return ms
+
+
+def measure_device(args, wl, rank, world, local_rank, sampler=None):
+    """Device-resident throughput of one workload: K-step regions replayed from CUDA graphs over a ring of simulator
+    states larger than L2, plus the two kernels alone.  Returns a dict of measurements (all times max over ranks)."""
     import torch.distributed as dist
 
+    from leibnizgym_b200.distributed import stats_to_sums
     from leibnizgym_b200.env import TrifingerEnv
     from leibnizgym_b200.graph_runner import GraphRunner
     from leibnizgym_b200.sim import SyntheticSim
-    from leibnizgym_b200.wrappers import VecTaskPython
+
+    dev = f"cuda:{local_rank}"
+    N, K, W = wl["envs"], args.steps, max(args.warmup, 3)
+    R = ring_slots(args, N)
+    asym = wl["asym"]
+    cfg = workload_config(wl, N * world)
+    ring = make_sequence(wl["seed"], R, N, device=dev, first_env=rank * N)
+    masks = bernoulli_masks(wl["seed"] + rank, R, N, wl["reset_p"], device=dev)
+    gmasks = bernoulli_masks(wl["seed"] + 7 + rank, R, N, wl.get("goal_p", 0.0), device=dev)
+    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(ring, dev), rank=rank, world_size=world)
+    env.reset()
+    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks, inject_goal_masks=gmasks)
+    timer = DeviceTimer(world, dev)
+    stream = torch.cuda.Stream()
+    side = torch.cuda.Stream() if world > 1 else None
+    out = {}
+    with torch.cuda.stream(stream):
+        # ---- graphs: K <= 1024 steps are ONE graph; longer regions replay a 128-step graph q times + a tail --------
+        if K <= 1024:
+            C, q, rem = K, 1, 0
+        else:
+            C = R * max(1, 128 // R)
+            q, rem = divmod(K, C)
+        main_graph = runner.capture(C)
+        tail_graph = runner.capture(rem) if rem else None
+        reduced = []
+
+        def region():
+            # Episode statistics are the path's only collective (SURVEY.md 8e).  Every timed region ends with the
+            # shard sums snapshotted on the step stream and all-reduced over NCCL on a side stream, the way a logger
+            # consumes them; the region is over only when that reduction has completed.
+            for _ in range(q):
+                main_graph.replay()
+            if tail_graph is not None:
+                tail_graph.replay()
+            if side is not None:
+                snap = stats_to_sums(env._step_stats, N)
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    dist.all_reduce(snap, op=dist.ReduceOp.SUM)
+                    snap.record_stream(side)
+                stream.wait_stream(side)
+                reduced[:] = [snap]
+
+        def lead_in():
+            main_graph.replay()
+
+        # ---- warm-up: at least W steps of exactly what is timed (every graph of the region replayed) ---------------
+        for _ in range(max(1, math.ceil(W / K))):
+            region()
+        timer.barrier()
+        if sampler is not None:
+            sampler.start()
+        ms = timer.run(region, lead_in, min_ms=args.min_timed_ms)
+        cold = [timer.once(region) for _ in range(min(len(ms), 15))]
+        cold_ms = timer.agree(statistics.median(cold))
+        # ---- the two kernels alone, back to back over the same ring (per-kernel roofline) --------------------------
+        Ck = R * max(1, 128 // R)
+        post_graph = runner.capture(Ck, post_only=True)
+        post_graph.replay()
+        post_ms = timer.run(post_graph.replay, post_graph.replay, min_ms=20.0, min_rep=9, max_rep=60)
+        pre_graph = runner.capture(Ck, pre_only=True)
+        pre_graph.replay()
+        pre_ms = timer.run(pre_graph.replay, pre_graph.replay, min_ms=10.0, min_rep=9, max_rep=60)
+        if sampler is not None:
+            sampler.stop()
+        # ---- sharded statistics: the NCCL all-reduce against a gather + host sum of the same vectors ----------------
+        if world > 1:
+            region()
+            torch.cuda.synchronize()
+            mine = stats_to_sums(env._step_stats, N)
+            parts = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            want = torch.stack(parts).cpu().sum(dim=0)
+            got = reduced[0].cpu()
+            err = float(((got - want).abs() / want.abs().clamp_min(1e-300)).max())
+            count_slots = [7, 8, 11, 12]   # position / orientation goal counts, resets, dones: integers, exact in fp64
+            counts_equal = bool(torch.equal(got[count_slots], want[count_slots]))
+            out["stats_allreduce_check"] = {"max_rel_err_vs_gathered_sum": err, "count_slots_equal": counts_equal,
+                                            "ok": bool(err < 1e-12 and counts_equal), "ranks": world}
+            if not out["stats_allreduce_check"]["ok"]:
+                raise RuntimeError(f"all-reduced statistics differ from the gathered per-rank sums: {out}")
+    med = statistics.median(ms)
+    out.update(
+        env=env, cfg=cfg, ring=R, ring_mib=ring.nbytes() / 2**20, steps_per_graph=C, repeats=len(ms),
+        region_ms=med, us_per_step=1e3 * med / K, us_p10=1e3 * pctl(ms, 0.1) / K, us_p90=1e3 * pctl(ms, 0.9) / K,
+        cold_us_per_step=1e3 * cold_ms / K,
+        post_us=1e3 * statistics.median(post_ms) / Ck, post_us_p10=1e3 * pctl(post_ms, 0.1) / Ck,
+        post_us_p90=1e3 * pctl(post_ms, 0.9) / Ck, pre_us=1e3 * statistics.median(pre_ms) / Ck,
+        value=float(K) * N * world / (med * 1e-3))
+    return out
+
+
+def summarize_workload(wl, m):
+    """Short record of one workload for `--all-workloads`."""
+    asym = wl["asym"]
+    N = wl["envs"]
+    peak, _ = hbm_peak()
+    post_gbs = POST_BYTES[asym] * N / (m["post_us"] * 1e-6) / 1e9
+    step_bytes = (POST_BYTES[asym] + PRE_BYTES + (wl["reset_p"] + wl.get("goal_p", 0.0) / 3) * RESET_BYTES) * N
+    return {"workload": wl["desc"], "envs_per_gpu": N, "value": m["value"], "us_per_step": m["us_per_step"],
+            "us_p10": m["us_p10"], "us_p90": m["us_p90"], "post_us": m["post_us"], "pre_us": m["pre_us"],
+            "post_frac_of_hbm_peak": post_gbs / peak,
+            "whole_step_frac_of_hbm_peak": step_bytes / (m["us_per_step"] * 1e-6) / 1e9 / peak,
+            "repeats": m["repeats"], "ring": m["ring"]}
+
+
+def run_gpu(args, wl):
+    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,120 +514,78 @@ def run_gpu(args, wl):
     if args.l2_fetch:
         from leibnizgym_b200 import _native as nat
         nat.check(nat.load().lg_set_l2_fetch_granularity(args.l2_fetch), "lg_set_l2_fetch_granularity")
-    N = wl["envs"]
-    K, W = args.steps, max(args.warmup, 3)
-    R = args.ring
+    N, K, W = wl["envs"], args.steps, max(args.warmup, 3)
     asym = wl["asym"]
-
-    cfg = workload_config(wl, N * world)
-    ring = make_sequence(wl["seed"], R, N, device=dev, first_env=rank * N)
-    masks = bernoulli_masks(wl["seed"] + rank, R, N, wl["reset_p"], device=dev)
-    gmasks = bernoulli_masks(wl["seed"] + 7 + rank, R, N, wl.get("goal_p", 0.0), device=dev)
-    env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(ring, dev), rank=rank, world_size=world)
-    env.reset()
-    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks, inject_goal_masks=gmasks)
-
-    stream = torch.cuda.Stream()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream), sampler:
-        C = R * max(1, 128 // R)          # steps per graph: whole ring, ~128 steps
-        q, rem = divmod(K, C)
-        runner.capture(C)
-        main_graph = runner.graph
-        tail_graph = None
-        if rem:
-            runner.capture(rem)
-            tail_graph = runner.graph
-        # ---- warm-up ---------------------------------------------------------------------------
-        for _ in range(max(1, math.ceil(W / C))):
-            main_graph.replay()
-        barrier()
-        # ---- timed region: exactly K steps -----------------------------------------------------
-        # Episode statistics are the path's only collective: every 512 steps the 16 shard sums are
-        # snapshotted on the step stream and all-reduced on a side stream, the way a logger consumes them — the
-        # steps do not wait for the other ranks; the timed region ends only when the last reduction has finished.
-        side = torch.cuda.Stream() if world > 1 else None
-        reduced = []
-        e0, e1 = ev(), ev()
-        e0.record()
-        for i in range(q):
-            main_graph.replay()
-            if world > 1 and (i % 4) == 3:
-                snap = env._step_stats.clone()
-                side.wait_stream(stream)
-                with torch.cuda.stream(side):
-                    dist.all_reduce(snap, op=dist.ReduceOp.SUM)
-                    snap.record_stream(side)
-                reduced.append(snap)
-        if tail_graph is not None:
-            tail_graph.replay()
-        if side is not None:
-            stream.wait_stream(side)
-        e1.record()
-        barrier()
-        step_ms_total = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([step_ms_total], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            step_ms_total = float(t.item())
-        # ---- dominant kernel alone (post_physics), same ring, same launch count -------------------
-        runner.capture(C, post_only=True)
-        post_graph = runner.graph
-        post_graph.replay()
-        torch.cuda.synchronize()
-        p0, p1 = ev(), ev()
-        reps = max(1, K // C)
-        p0.record()
-        for _ in range(reps):
-            post_graph.replay()
-        p1.record()
-        torch.cuda.synchronize()
-        post_us = 1e3 * p0.elapsed_time(p1) / (reps * C)
+    # clocks are sampled on rank 0 only (one NVML thread per box, 20 ms period), while the timed repeats run
+    sampler = ClockSampler(physical_gpu_index(local_rank), period_s=0.02) if rank == 0 else None
+    m = measure_device(args, wl, rank, world, local_rank, sampler)
+    m.pop("env")
+    cfg = m.pop("cfg")
+    clocks = sampler.summary() if sampler is not None else None
 
     # ---- end to end through the public API with host buffers (rank-local, then max over ranks) ----
-    with NumaBinding(physical_gpu_index(local_rank)) as numa:
-        e2e = run_e2e(args, wl, cfg, dev, rank, world)
-    e2e["host_numa"] = numa.info
-    clocks = sampler.summary()
+    if args.no_e2e:
+        e2e = None
+    else:
+        with NumaBinding(physical_gpu_index(local_rank)) as numa:
+            e2e = run_e2e(args, wl, cfg, dev, rank, world)
+        e2e["host_numa"] = numa.info
 
-    total_env_steps = float(K) * N * world
-    value = total_env_steps / (step_ms_total * 1e-3)
     peak, peak_src = hbm_peak()
     post_bytes = POST_BYTES[asym] * N
+    post_us = m["post_us"]
     achieved = post_bytes / (post_us * 1e-6) / 1e9
-    step_bytes = (POST_BYTES[asym] + PRE_BYTES + wl["reset_p"] * RESET_BYTES) * N
+    step_bytes = (POST_BYTES[asym] + PRE_BYTES + (wl["reset_p"] + wl.get("goal_p", 0.0) / 3) * RESET_BYTES) * N
+    step_s = m["us_per_step"] * 1e-6
+    config = make_config(wl, world, m["ring"], m["ring_mib"])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": step_ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_gpu": N, "global_envs": N * world, "parallelism": f"dp{world}",
-                   "l2_policy": f"inputs larger than L2: ring of {R} distinct simulator states "
-                                f"({ring.nbytes() / 2**20:.0f} MiB) and {R} output slots per GPU",
-                   "steps_per_graph": C, "reset_fraction_per_step": wl["reset_p"],
-                   "goal_reset_fraction_per_step": wl.get("goal_p", 0.0),
-                   "extensions": [k for k in ("dr", "keypoint") if wl.get(k)]},
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": m["us_per_step"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
+        "timing": {"method": "CUDA events around the K-step region replayed from CUDA graphs, after one untimed lead-in "
+                             "replay (steady state); barrier + synchronize around every repeat; per repeat the max over "
+                             "ranks; value = median over repeats",
+                   "repeats": m["repeats"], "steps_per_graph": m["steps_per_graph"], "region_ms_median": m["region_ms"],
+                   "us_per_step_median": m["us_per_step"], "us_per_step_p10": m["us_p10"], "us_per_step_p90": m["us_p90"],
+                   "cold_start_us_per_step": m["cold_us_per_step"],
+                   "statistics_allreduce_in_region": world > 1},
         "roofline": {"bound": "hbm", "kernel": "post_physics_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N, asym), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,
-                     "whole_step_gbs": step_bytes / (step_ms_total / K * 1e-3) / 1e9},
+                     "launch_us_p10": m["post_us_p10"], "launch_us_p90": m["post_us_p90"],
+                     "pre_us": m["pre_us"], "pre_algorithmic_bytes_per_launch": PRE_BYTES * N,
+                     "step_us": m["us_per_step"], "whole_step_gbs": step_bytes / step_s / 1e9,
+                     "whole_step_frac": step_bytes / step_s / 1e9 / peak},
         "clocks": clocks,
-        "e2e": e2e,
         "gpu_launches": 2 * K * world,
     }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if "stats_allreduce_check" in m:
+        line["stats_allreduce_check"] = m["stats_allreduce_check"]
+    if args.all_workloads:
+        per = {args.workload: summarize_workload(wl, m)}
+        for name in ALL_WORKLOADS:
+            if name == args.workload:
+                continue
+            w2 = dict(WORKLOADS[name])
+            torch.cuda.empty_cache()
+            m2 = measure_device(args, w2, rank, world, local_rank)
+            m2.pop("env"), m2.pop("cfg")
+            per[name] = summarize_workload(w2, m2)
+        line["workloads"] = per
     if rank == 0 and world == 1 and not args.no_cpu:
         r = time_cpu_path(wl, N, steps=10_000, warmup=3, max_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {
             "value": r["env_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
             "sample": f"{r['steps']} steps x {N} envs (~{args.cpu_seconds:.0f} s), oracle port of the reference's torch CPU "
                       f"path, simulator playback excluded"}
+        if args.all_workloads:   # BASELINE config 1 is the reference's own CPU-runnable case: time it on the CPU too
+            for name in ("c1", "c1sym"):
+                w1 = WORKLOADS[name]
+                r1 = time_cpu_path(w1, w1["envs"], steps=10_000, warmup=3, max_seconds=min(args.cpu_seconds, 6.0))
+                line["workloads"][name]["cpu_env_steps_per_s"] = r1["env_steps_per_s"]
+                line["workloads"][name]["cpu_ms_per_step"] = r1["ms_per_step"]
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -499,12 +674,16 @@ def run_e2e(args, wl, cfg, dev, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20480)
-    ap.add_argument("--warmup", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=256)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="override envs per GPU")
-    ap.add_argument("--ring", type=int, default=32, help="distinct simulator states in HBM")
+    ap.add_argument("--ring", type=int, default=0, help="distinct simulator states in HBM (0: sized to several times L2)")
+    ap.add_argument("--all-workloads", action="store_true",
+                    help="also measure one line per BASELINE.json config (c1, c1sym, c2, c3ref, c4, c5) into `workloads`")
+    ap.add_argument("--min-timed-ms", type=float, default=50.0, help="repeat the K-step region until this much device time is covered")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-mode", default="copy", choices=["zc", "zc_out", "copy"])
     ap.add_argument("--e2e-chunks", type=int, default=1, help="env ranges of the host pipeline (0 = un-chunked copies)")

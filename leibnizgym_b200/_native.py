@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libleibniz_b200.so")
+# LG_LIB_PATH: development hook for same-box A/B runs of two builds of this library (scripts/ab_bench.sh)
+LIB_PATH = os.environ.get("LG_LIB_PATH") or os.path.join(_HERE, "libleibniz_b200.so")
 
 LG_MAX_ACTION_DIM = 18
 LG_MAX_STATE_DIM = 122

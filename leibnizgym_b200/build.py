@@ -43,18 +43,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > out_m for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, defines=(), output: str = None) -> str:
+    """`defines` / `output`: development builds (e.g. -DLG_TRACE into ab/trace.so); the shipped library takes neither."""
+    if output is None and not defines and not force and not needs_build():
         return OUTPUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUTPUT, *SOURCES]
+    out = output or OUTPUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-o", out, *SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         print(res.stderr)
-    return OUTPUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m leibnizgym_b200.build [--force] [-v] [-DNAME[=V] ...] [-o path]
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outp = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, output=outp))

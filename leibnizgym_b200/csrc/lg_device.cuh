@@ -15,6 +15,22 @@
 
 namespace lg {
 
+// Development-only phase tracing (-DLG_TRACE, scripts/trace_step.py): lane 0 of selected warps stamps %globaltimer
+// and the SM clock at named points of the two step kernels; never compiled into the shipped library.
+#ifdef LG_TRACE
+constexpr int kTraceSlots = 24, kTraceMaxCtas = 8192;
+__device__ unsigned long long g_trace[2][kTraceMaxCtas][2 * kTraceSlots];
+__device__ __forceinline__ void trace_point(int kernel, int slot) {
+  unsigned long long t, c;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+  if (blockIdx.x < kTraceMaxCtas) { g_trace[kernel][blockIdx.x][slot] = t; g_trace[kernel][blockIdx.x][kTraceSlots + slot] = c; }
+}
+#define LG_TP(kernel, slot, cond) do { if (cond) trace_point(kernel, slot); } while (0)
+#else
+#define LG_TP(kernel, slot, cond) do { } while (0)
+#endif
+
 constexpr float kTwoPi = 6.283185307179586f;  // fp32(2 * np.pi), envs/trifinger/sample.py:29, :82
 
 // ---------------------------------------------------------------------------------------

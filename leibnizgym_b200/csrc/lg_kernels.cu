@@ -498,6 +498,17 @@ int lg_step_host_pipelined(const LgParams* P, const LgSimState* S, const LgBuffe
   return check_launch("lg_step_host_pipelined");
 }
 
+#ifdef LG_TRACE
+// development only: copies the phase stamps of kernel `which` (0 post, 1 pre) to host memory
+int lg_trace_read(int which, unsigned long long* dst, int ctas) {
+  if (which < 0 || which > 1 || ctas > lg::kTraceMaxCtas) return fail(LG_ERR_BAD_ARG, "bad trace request");
+  const size_t bytes = sizeof(unsigned long long) * 2 * lg::kTraceSlots * (size_t)ctas;
+  if (cudaMemcpyFromSymbol(dst, lg::g_trace, bytes, sizeof(unsigned long long) * 2 * lg::kTraceSlots * lg::kTraceMaxCtas * which) != cudaSuccess)
+    return check_launch("lg_trace_read");
+  return LG_OK;
+}
+#endif
+
 int lg_step_host(const LgParams* P, const LgSimState* S, const LgBuffers* B, const LgHostStep* H, double sched_step, void* stream) {
   if (int rc = validate(P, S, B, true)) return rc;
   if (!H || !H->dof_state_host || !H->root_state_host || !H->rigid_body_host || !H->action_host || !H->action_staging ||

@@ -257,6 +257,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   const int tid = threadIdx.x;
   const int64_t e0 = (int64_t)blockIdx.x * E;
   const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
+  LG_TP(0, 0, tid == 0); LG_TP(0, 12, tid == 128);
 
   // ---- role of this lane ---------------------------------------------------------------------------
   int role = tid % R::LANES;
@@ -292,6 +293,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   }
   src += (e0 + env_first) * stride;
   pdl_wait();  // everything above is independent of the previous kernel's results
+  LG_TP(0, 1, tid == 0); LG_TP(0, 13, tid == 128);
   const int cnt = max(0, min(EP, nvalid - env_first));   // envs of this lane: env_first .. env_first + cnt - 1
   const bool full = nvalid == E;                           // every CTA but possibly the last
 
@@ -325,6 +327,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   }
 
   pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
+  LG_TP(0, 2, tid == 0);
 
   // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----
   if (tid < C_COUNT) s_coef[tid] = (REWARD && P.use_device_clock) ? __ldg(B.reward_coef + tid) : CF.v[tid];
@@ -374,7 +377,9 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
         if (k < cnt) dst[k * stage_stride] = v[k];
     }
   }
+  LG_TP(0, 3, tid == 0);
   __syncthreads();
+  LG_TP(0, 4, tid == 0); LG_TP(0, 14, tid == 128);
 
   // ---- phase 3 (all warps; the reward warps come back to it after their math) -------------------------
   auto emit_outputs = [&](auto full_c) {
@@ -524,7 +529,9 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
         s_part[8 + rw][env] = acc;
       }
     }
+    LG_TP(0, 5, tid == 0); LG_TP(0, 16, tid == 32); LG_TP(0, 17, tid == 64); LG_TP(0, 18, tid == 96);
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four reward warps
+    LG_TP(0, 6, tid == 0);
   }
   if (REWARD && rw == 0) {
     // ---- warp 0: combine, terminate, count (one lane per env) -----------------------------------------
@@ -584,6 +591,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       st[LG_STAT_RESETS] = reset;
       st[LG_STAT_DONES] = dn;
     }
+    LG_TP(0, 7, tid == 0);
     // ---- episode statistics: per-CTA fp64 sums in a fixed order, one RED per slot, no fence ----------
     if (env < E) {  // lanes beyond the tile hold nothing (E < 32)
 #pragma unroll
@@ -606,9 +614,11 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
       if (is_mean) acc = acc / (double)(P.stats_num_envs > 0 ? P.stats_num_envs : P.num_envs);
       atomicAdd(B.step_stats + env, acc);
     }
+    LG_TP(0, 8, tid == 0);
   }
   if (full) emit_outputs(std::true_type{});
   else emit_outputs(std::false_type{});
+  LG_TP(0, 9, tid == 0); LG_TP(0, 15, tid == 128); LG_TP(0, 19, tid == 32); LG_TP(0, 20, tid == 64); LG_TP(0, 21, tid == 96);
 }
 
 // history seeding (trifinger_env.py:619-628): both entries = initial simulator state

@@ -147,6 +147,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   // previous launch, the action and the joint state by the caller / simulator — all complete before the preceding
   // post-physics pass was allowed past its own dependency wait.
   // every thread reads the epoch before the tile publishes anything, so the last tile may advance it
+  LG_TP(1, 0, tid == 0);
   const uint32_t epoch = ld_volatile_u32(&B.control->scan_epoch);
   int tile = blockIdx.x;
   if (TICKET) {  // grids larger than what is co-resident: tiles by ticket, so predecessors always run
@@ -177,7 +178,9 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
       for (int c = 0; c < 18; ++c) s_dof[tid * 18 + c] = S.dof_state[e * 18 + c];
     }
   }
+  LG_TP(1, 1, tid == 0);
   pdl_wait();   // the flags, counters and statistics below are results of the preceding post-physics pass
+  LG_TP(1, 2, tid == 0);
   uint8_t flag_r = 0, flag_g = 0;
   if (live) {
     flag_r = B.reset[e]; flag_g = B.goal_reset[e];
@@ -201,6 +204,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned ba = __ballot_sync(0xffffffffu, f_reset), bb = __ballot_sync(0xffffffffu, f_goal);
   if (lane == 0) { s_wa[warp] = __popc(ba); s_wb[warp] = __popc(bb); }
+  LG_TP(1, 3, tid == 0);
   __syncthreads();   // also orders the mbarrier initialisation before the waits below
   TileScan t;
   t.tile = tile; t.epoch = epoch;
@@ -225,7 +229,9 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   const bool need_rank_first = P.inject_draws != 0;  // injected draws are indexed by compaction rank
   if (need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
 
+  LG_TP(1, 4, tid == 0);
   if (full_tile) mbar_wait(&s_mbar, 0);   // the slabs have landed (each thread only touches its own env row below)
+  LG_TP(1, 5, tid == 0);
 
   // ---- this env's action row: noise (extension), clamp, reset ---------------------------------------
   float act[A];
@@ -263,6 +269,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   // are listed in shared memory by their rank in the tile, then each WARP runs two of the eight reset sub-tasks over
   // that list (lane = listed env): uniform control flow, and a serial chain of ~2 Philox blocks per warp instead of
   // ten per resetting thread.
+  LG_TP(1, 6, tid == 0);
   if ((t.total_a | t.total_b) != 0) {
     __shared__ uint16_t s_reset_list[E], s_goal_list[E];
     if (f_reset) s_reset_list[t.rank_a] = (uint16_t)(tid | (f_goal ? 0x8000 : 0));
@@ -296,6 +303,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   }
   // ---- moving goal (__update_goal_movement_pre, trifinger_env.py:1267-1277): every step the goal body's
   // angular velocity is re-imposed from the movement buffer (freshly sampled above for envs that reset)
+  LG_TP(1, 7, tid == 0);
   if (P.goal_rotation && live) {
     float* row = S.root_state + (P.actors_per_env * e + P.goal_slot) * 13;
     const float* gm = B.goal_movement + e * 6;
@@ -309,6 +317,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   // next to this kernel's one warp per scheduler and slows the latency chain above; measured, us/step at 16k envs /
   // 30 % resets: right after the flag loads 11.50 / 16.95, after the slab wait 11.38 / 16.83, here 11.28 / 16.50,
   // no explicit trigger 11.98 / 17.24.
+  LG_TP(1, 8, tid == 0);
   pdl_launch_dependents();
   if (full_tile) {
     fence_async_proxy();           // generic-proxy writes to the slabs -> visible to the bulk-copy engine
@@ -327,6 +336,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     }
   }
 
+  LG_TP(1, 9, tid == 0);
   // ---- ordered id lists (env_base.py:374-379; trifinger_env.py:413-416, :435-436) ---------------
   if (!need_rank_first) tile_scan_finish<TICKET>(B.control, B.scan_status, t, num_tiles, ex_a, ex_b, B.counts);
   if (f_reset) {
@@ -346,7 +356,9 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
   }
   // shared memory must outlive the bulk stores that read it
+  LG_TP(1, 10, tid == 0);
   if (full_tile && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  LG_TP(1, 11, tid == 0);
 }
 
 // standalone compaction (torch.nonzero(mask).view(-1))

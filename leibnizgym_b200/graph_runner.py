@@ -72,34 +72,38 @@ class GraphRunner:
         self.t0 = 0  # ring cursor of the runner's first step (host clock only)
 
     # -- one step, eager (also what gets captured) -----------------------------------------
-    def _launch_step(self, t: int, stream: int, post_only: bool = False) -> None:
+    def _launch_step(self, t: int, stream: int, post_only: bool = False, pre_only: bool = False) -> None:
         s = t % self.R
         prev = (t - 1) % self.R
         if not post_only:
             # resets write into the tensors the simulator consumes next (slot of the previous state)
             nat.check(self.lib.lg_pre_physics(self.P, self._S[prev], self._B[prev],
                                               self.ring.action[s].data_ptr(), stream), "lg_pre_physics")
+        if pre_only:
+            return
         sched = 0.0 if self.device_clock else float((self.frame0 + (t - self.t0) + 1) * self.env._global_N)
         nat.check(self.lib.lg_post_physics(self.P, self._S[s], self._B[s], sched, stream), "lg_post_physics")
 
-    def step_eager(self, n: int = 1, post_only: bool = False) -> None:
+    def step_eager(self, n: int = 1, post_only: bool = False, pre_only: bool = False) -> None:
         stream = torch.cuda.current_stream().cuda_stream
         for _ in range(n):
-            self._launch_step(self.t, stream, post_only)
+            self._launch_step(self.t, stream, post_only, pre_only)
             self.t += 1
 
     # -- graph ----------------------------------------------------------------------------------
-    def capture(self, steps: int, post_only: bool = False) -> None:
+    def capture(self, steps: int, post_only: bool = False, pre_only: bool = False) -> torch.cuda.CUDAGraph:
         """Captures `steps` consecutive steps starting at ring slot 0 (steps % R == 0 keeps replays
-        aligned with the ring)."""
-        self.step_eager(2, post_only)  # warm: module load, first-touch
+        aligned with the ring).  `post_only` / `pre_only`: one of the two kernels alone, back to back
+        (per-kernel timing).  Returns the graph (also kept as `self.graph`)."""
+        self.step_eager(2, post_only, pre_only)  # warm: module load, first-touch
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             stream = torch.cuda.current_stream().cuda_stream
             for t in range(steps):
-                self._launch_step(t, stream, post_only)
+                self._launch_step(t, stream, post_only, pre_only)
         self.graph, self.steps_per_graph = g, steps
+        return g
 
     def replay(self, times: int = 1) -> None:
         for _ in range(times):
