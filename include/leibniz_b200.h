@@ -239,6 +239,10 @@ int lg_build_role_table(const LgParams* P, const LgBuffers* B, void* stream);
 
 /* number of look-back status words lg_pre_physics needs for n envs */
 int64_t lg_scan_tiles(int64_t num_envs);
+/* Largest tile count whose pre-physics CTAs are all co-resident on the current device (occupancy of the kernel x SM
+ * count).  Shards with more tiles take their tiles by ticket (dispatch order) instead of by block index; results are
+ * identical, the value is exposed for tests and capacity planning.  Needs a CUDA device. */
+int64_t lg_pre_resident_tiles(void);
 
 /*
  * Everything IsaacEnvBase.step does BEFORE physics (envs/env_base.py:369-381), one launch:

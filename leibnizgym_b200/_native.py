@@ -103,6 +103,7 @@ SYMBOLS = {
     "lg_last_error": (C.c_char_p, []),
     "lg_struct_size": (C.c_size_t, [C.c_int]),
     "lg_scan_tiles": (_i64, [_i64]),
+    "lg_pre_resident_tiles": (_i64, []),
     "lg_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "lg_build_role_table": (C.c_int, [_P, _B, _vp]),
     "lg_pre_physics": (C.c_int, [_P, _S, _B, _vp, _vp]),

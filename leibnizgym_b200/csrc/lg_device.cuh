@@ -18,7 +18,7 @@ namespace lg {
 // Development-only phase tracing (-DLG_TRACE, scripts/trace_step.py): lane 0 of selected warps stamps %globaltimer
 // and the SM clock at named points of the two step kernels; never compiled into the shipped library.
 #ifdef LG_TRACE
-constexpr int kTraceSlots = 24, kTraceMaxCtas = 8192;
+constexpr int kTraceSlots = 32, kTraceMaxCtas = 8192;
 __device__ unsigned long long g_trace[2][kTraceMaxCtas][2 * kTraceSlots];
 __device__ __forceinline__ void trace_point(int kernel, int slot) {
   unsigned long long t, c;
@@ -36,16 +36,29 @@ constexpr float kTwoPi = 6.283185307179586f;  // fp32(2 * np.pi), envs/trifinger
 // ---------------------------------------------------------------------------------------
 // memory helpers
 // ---------------------------------------------------------------------------------------
-// streaming 128-bit load: read-only path, no L1 allocation (every input byte is used once)
+// streaming 128-bit load: read-only path, no L1 allocation (every input byte is used once).  Only for tensors the
+// calling kernel never writes (simulator rows in the post-physics pass).
 __device__ __forceinline__ float4 ld_stream4(const float4* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// the same without the read-only path: for rows the SAME kernel rewrites later (the history entry), where
+// ld.global.nc would be outside the PTX contract (.nc data must not change during the kernel)
+__device__ __forceinline__ float4 ld_hist4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// 32-bit load of a column element: no L1 allocation (every input byte is used once), 64-byte L2 fetches (the gathered
+// 52-byte rows cost 25 % fewer DRAM sectors than with the default granularity).  Not the read-only `.nc` path: the
+// goal-pose column is rewritten by the same kernel in the moving-goal path, and `.nc` data must not change while
+// the kernel runs.
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
@@ -295,8 +308,8 @@ __device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource&
 
 // Writes the sampled goal into the goal buffers and the goal actor's root row
 // (trifinger_env.py:1248-1265).
-__device__ __forceinline__ void apply_goal_sample(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                                  int64_t e, const DrawSource& dr, const float* ub5 = nullptr) {
+__device__ __noinline__ void apply_goal_sample(const LgParams& P, const LgSimState& S, const LgBuffers& B,
+                                               int64_t e, const DrawSource& dr, const float* ub5 = nullptr) {
   float pose[7], angvel[3], u5[4];
   if (ub5) { u5[1] = ub5[1]; u5[2] = ub5[2]; u5[3] = ub5[3]; }
   else dr.uniform4(5, u5);                      // goal columns 21..23 live in uniform block 5
@@ -323,9 +336,11 @@ __device__ __forceinline__ void apply_goal_sample(const LgParams& P, const LgSim
 constexpr int kResetSubtasks = 8;
 // `dof_mirror`: optional second destination of the env's new joint-state row (the fused kernel's shared-memory copy,
 // from which the torque is computed right afterwards).
-__device__ __forceinline__ void reset_subtask(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
-                                              int sub, const DrawSource& dr, bool goal_reset_follows,
-                                              float* dof_mirror = nullptr) {
+// Out of line on purpose: the fused kernel reaches it from several call sites behind a block-uniform branch that most
+// tiles never take; one copy keeps the kernel's hot path (no resets) small enough to sit in the instruction cache.
+__device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
+                                           int sub, const DrawSource& dr, bool goal_reset_follows,
+                                           float* dof_mirror = nullptr) {
   if (sub < 5) {
     if (P.robot_reset == LG_RESET_NONE) return;
     float* dof = S.dof_state + e * 18;

@@ -134,10 +134,11 @@ int sm_count() {
   return n;
 }
 
-// bit 0: pre-physics kernel launched programmatically, bit 1: post-physics kernel.  Measured on B200 (us/step):
-// 16k envs, no resets: post only 11.5-11.7, both 11.4-11.5, none 11.9; 30 % resets: post only 17.5, both 21.6 —
-// a long pre-physics pass should not have the post pass's CTAs parked on the SMs, so the default is post only.
-int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : env_int("LG_PDL", 2); return m; }
+// Programmatic dependent launch of the post-physics kernel (LG_PDL=0 / LG_NO_PDL=1 switch it off).  The pre-physics
+// kernel is always launched in stream order: launching it programmatically as well measured no gain without resets
+// and 21.6 instead of 17.5 us/step with 30 % resets in round 1 (a long pre-physics pass should not have the post
+// pass's CTAs parked on the SMs), and is not supported by the two-group kernel of round 2.
+int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : (env_int("LG_PDL", 2) & 2); return m; }
 
 // Launch with programmatic stream serialisation (PDL) unless LG_NO_PDL is set.
 template <typename... KArgs, typename... Args>
@@ -220,6 +221,11 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
                      (table_mode == 2 || (table_mode == 1 && (int64_t)grid > (int64_t)sm_count() * 4));
   if (table && !aligned16(B->role_table)) return fail(LG_ERR_BAD_ARG, "role_table must be 16-byte aligned");
 #define LG_X(AD, AS, CL, EE, EX, TB) launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, EX, REWARD && TB>, grid, lg::kPostThreads, st, *P, *S, *B, cf)
+#ifdef LG_FAST_BUILD
+  if (ext || clip || table || P->action_dim != 9) return fail(LG_ERR_UNSUPPORTED, "LG_FAST_BUILD: instantiation not built");
+  if (asym) err = E == 28 ? LG_X(9, true, false, 28, false, false) : LG_X(9, true, false, 32, false, false);
+  else err = E == 28 ? LG_X(9, false, false, 28, false, false) : LG_X(9, false, false, 32, false, false);
+#else
 #define LG_T(AD, AS, CL, EE, EX) (table ? LG_X(AD, AS, CL, EE, EX, true) : LG_X(AD, AS, CL, EE, EX, false))
 #define LG_K(AD, AS, CL, EE) (ext ? LG_T(AD, AS, CL, EE, true) : LG_T(AD, AS, CL, EE, false))
 #define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))
@@ -230,9 +236,12 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
     if (asym) err = clip ? LG_K(18, true, true, 32) : LG_K(18, true, false, 32);
     else err = clip ? LG_K(18, false, true, 32) : LG_K(18, false, false, 32);
   }
+#endif
+#ifndef LG_FAST_BUILD
 #undef LG_E
 #undef LG_K
 #undef LG_T
+#endif
 #undef LG_X
   if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("post_physics_kernel: ") + cudaGetErrorString(err));
   return check_launch("post_physics_kernel");
@@ -259,7 +268,15 @@ size_t lg_struct_size(int which) {
     default: return 0;
   }
 }
-int64_t lg_scan_tiles(int64_t n) { return (n + lg::kPreThreads - 1) / lg::kPreThreads; }
+int64_t lg_scan_tiles(int64_t n) { return (n + lg::kPreTile - 1) / lg::kPreTile; }
+int64_t lg_pre_resident_tiles(void) {
+  int per_sm9 = 0, per_sm18 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, lg::pre_physics_kernel<9, false>, lg::kPreThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm18, lg::pre_physics_kernel<18, false>, lg::kPreThreads, 0);
+  const int per_sm = per_sm9 < per_sm18 ? per_sm9 : per_sm18;
+  cudaGetLastError();   // no device: report one CTA per SM of the default count rather than an error
+  return (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
+}
 
 int lg_post_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, double sched_step, void* stream) {
   return launch_post<true>(P, S, B, sched_step, (cudaStream_t)stream);
@@ -303,8 +320,13 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
   const int tiles = (int)lg_scan_tiles(P->num_envs);
   if (!aligned16(action_in)) return fail(LG_ERR_BAD_ARG, "action_in must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  // all tiles co-resident (<= 8 CTAs on each of 148 SMs): tiles are block indices; beyond that, tickets
-  const bool ticket = tiles > 148 * 8;
+  // The look-back spins on predecessor tiles, so every tile a CTA can wait for must be running: while the whole grid
+  // is co-resident (lg_pre_resident_tiles) tiles are block indices; larger grids take their tiles by ticket, in
+  // dispatch order.  (The post pass's CTAs cannot crowd this kernel out: they are only launched once every CTA of
+  // this grid has started.)  LG_PRE_TICKET=1 forces the ticket path (tests).
+  static const int64_t resident_ctas = lg_pre_resident_tiles();
+  static const bool force_ticket = env_flag("LG_PRE_TICKET");
+  const bool ticket = force_ticket || tiles > resident_ctas;
 cudaError_t err;
 #define LG_PRE(AD, TK) err = launch_pdl(pdl_mode() & 1, lg::pre_physics_kernel<AD, TK>, (unsigned)tiles, lg::kPreThreads, st, *P, *S, *B, action_in, tiles)
   if (P->action_dim == 9) { if (ticket) LG_PRE(9, true); else LG_PRE(9, false); }
@@ -320,7 +342,7 @@ int lg_compact(const uint8_t* mask, int64_t n, int64_t* ids_out, int32_t* count_
   if (n < 0 || n >= (1 << 23)) return fail(LG_ERR_BAD_ARG, "n out of range");
   if (n == 0) { cudaMemsetAsync(count_out, 0, 2 * sizeof(int32_t), (cudaStream_t)stream); return check_launch("memset"); }
   const int tiles = (int)lg_scan_tiles(n);
-  lg::compact_kernel<<<tiles, lg::kPreThreads, 0, (cudaStream_t)stream>>>(mask, n, ids_out, count_out, status, control, tiles);
+  lg::compact_kernel<<<tiles, lg::kScanThreads, 0, (cudaStream_t)stream>>>(mask, n, ids_out, count_out, status, control, tiles);
   return check_launch("compact_kernel");
 }
 

@@ -28,7 +28,7 @@ import yaml
 from . import _native as nat
 from .config import resolve_config
 from .params import action_dim_of, action_scale, build_params, observation_scale, state_scale
-from .sim import SyntheticSim
+from .sim import LazyCount, SyntheticSim
 from .synthetic import make_sequence
 
 
@@ -78,30 +78,6 @@ class IsaacEnvBase:
         self._steps_count_buf = torch.zeros(N, device=dev, dtype=torch.long)
 
     # -- getters (ref env_base.py:222-255) ---------------------------------------------
-    # -- simulator control plane (ref env_base.py:175-220): owned by the simulator object, forwarded when it has them
-    def _sim_call(self, name: str, *args):
-        fn = getattr(getattr(self, "_sim", None), name, None)
-        if fn is None:
-            raise NotImplementedError(f"the simulator object does not provide `{name}` (physics is out of this package's scope)")
-        return fn(*args)
-
-    def set_gravity(self, gravity=(0, 0, -9.81)):
-        self.config["sim"]["gravity"] = [float(g) for g in gravity]
-        if hasattr(getattr(self, "_sim", None), "set_gravity"):
-            self._sim.set_gravity(gravity)
-
-    def get_gravity(self) -> np.ndarray:
-        return np.asarray(self.config["sim"]["gravity"], dtype=np.float64)
-
-    def set_sim_params(self, params):
-        return self._sim_call("set_sim_params", params)
-
-    def get_sim_params(self):
-        return self._sim_call("get_sim_params")
-
-    def set_camera_lookat(self, pos, target):
-        return self._sim_call("set_camera_lookat", pos, target)
-
     def get_state_shape(self) -> torch.Size:
         return self._states_buf.size()
 
@@ -527,6 +503,7 @@ class TrifingerEnv(IsaacEnvBase):
         self._P.fuse_bookkeeping = 1
         nat.check(self._lib.lg_pre_physics(self._P, self._S, self._B, action.data_ptr(), self._stream()), "lg_pre_physics")
         self._clear_injection()
+        self._notify_resets()
         self._sim.set_dof_actuation_force_tensor(self._applied_torque)
         self._notify_goal_movement()
         for _ in range(self.control_decimation):
@@ -600,6 +577,17 @@ class TrifingerEnv(IsaacEnvBase):
         self._call("lg_pre_step", self._P, self._S, self._B)
         self._sim.set_dof_actuation_force_tensor(self._applied_torque)
         self._notify_goal_movement()
+
+    def _notify_resets(self):
+        """Tell the simulator which rows the pre-physics pass rewrote — what `_reset_impl` / `_goal_reset_impl` end
+        with in the reference (`set_dof_state_tensor_indexed`, `set_actor_root_state_tensor_indexed`,
+        trifinger_env.py:413-423, :435-440), in the same order.  The index lists and their lengths stay on the
+        device (`LazyCount`): the step itself never synchronises; an adapter that needs a host integer calls
+        `int(count)`.  Unlike the reference the calls are made every step, also when nothing was reset (count 0)."""
+        n_reset = LazyCount(self._counts[0])
+        self._sim.set_dof_state_tensor_indexed(self._robot_indices, n_reset)
+        self._sim.set_actor_root_state_tensor_indexed(self._reset_root_indices, LazyCount(self._counts[0], 3))
+        self._sim.set_actor_root_state_tensor_indexed(self._goal_root_indices, LazyCount(self._counts[1]))
 
     def _notify_goal_movement(self):
         """Moving goal (ref trifinger_env.py:1267-1277): the kernels re-imposed every goal body's angular velocity;

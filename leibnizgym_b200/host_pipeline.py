@@ -79,5 +79,6 @@ class HostPipeline:
         nat.check(self.lib.lg_step_host_pipelined(env._P, env._S, env._B, H, float(env.env_steps_count), self.chunks,
                                                   main, *self._streams), "lg_step_host_pipelined")
         env._clear_injection()
+        env._notify_resets()
         env._step_info = env._make_info()
         return self.h_obs, self.h_reward, self.h_dones, env._step_info

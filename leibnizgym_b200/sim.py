@@ -20,6 +20,29 @@ import torch
 from .synthetic import StateSequence
 
 
+class LazyCount:
+    """Number of valid entries of a device-side index list, known only on the device until somebody asks.
+
+    The fused step compacts the reset flags on the GPU and never synchronises the host, so the count the reference
+    passes to `set_*_tensor_indexed` as a Python int (`len(indices)`, ref trifinger_env.py:419-423, :437-440) exists
+    as a device scalar.  The simulator adapter decides how to consume it: `int(count)` reads it back (one stream
+    synchronisation, what the reference pays anyway), `count.device_scalar` / `count.scale` feed an API that takes
+    device-side counts."""
+
+    __slots__ = ("device_scalar", "scale")
+
+    def __init__(self, device_scalar: torch.Tensor, scale: int = 1):
+        self.device_scalar, self.scale = device_scalar, int(scale)
+
+    def __int__(self) -> int:
+        return int(self.device_scalar.item()) * self.scale
+
+    __index__ = __int__
+
+    def __repr__(self) -> str:
+        return f"LazyCount({self.scale} x device scalar)"
+
+
 class SyntheticSim:
     def __init__(self, seq: StateSequence, device: str = "cuda:0"):
         self.seq = seq

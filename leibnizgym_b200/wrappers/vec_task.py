@@ -95,12 +95,18 @@ class VecTask:
 
 class VecTaskPython(VecTask):
     def __init__(self, task: IsaacEnvBase, rl_device: str, clip_obs: float = 5.0, clip_actions: float = 1.0,
-                 host_pipeline_chunks: int = 0, obs_dtype: torch.dtype = torch.float32):
+                 host_pipeline_chunks: int = 0, obs_dtype: torch.dtype = torch.float32, blocking: bool = True):
         """`host_pipeline_chunks` > 0 (host-resident simulator and learner, rl_device 'cpu'): step through
         host_pipeline.HostPipeline, which overlaps the state upload, the kernels and the result download.
-        `obs_dtype=torch.bfloat16`: hand the learner bf16 observations / states, emitted by the fused pass itself."""
+        `obs_dtype=torch.bfloat16`: hand the learner bf16 observations / states, emitted by the fused pass itself.
+        `blocking` (host-resident results only): `step()` returns once the results ARE in the returned pinned host
+        tensors and the kernels have consumed the caller's action buffer — what the reference's blocking
+        `.to(rl_device)` copies guarantee (ref wrappers/vec_task.py:164-170).  `blocking=False` returns as soon as
+        the work is enqueued; the caller then owns the stream synchronisation before it reads the results or
+        overwrites a pinned action buffer it passed in."""
         super().__init__(task, rl_device, clip_obs, clip_actions)
         self._pipeline = None
+        self._blocking = bool(blocking)
         if obs_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("obs_dtype must be torch.float32 or torch.bfloat16")
         self._bf16 = obs_dtype == torch.bfloat16
@@ -120,6 +126,11 @@ class VecTaskPython(VecTask):
             if self._bf16:
                 task.enable_bf16_outputs()
 
+    def _host_results_ready(self) -> None:
+        """Host-resident results: wait until the step's kernels / copies have completed (see `blocking`)."""
+        if self._blocking:
+            torch.cuda.current_stream(self._task._torch_device).synchronize()
+
     def get_state(self) -> torch.Tensor:
         if self._pipeline is not None:
             return self._pipeline.h_states
@@ -137,11 +148,15 @@ class VecTaskPython(VecTask):
         if self._task.visualize:
             self._task.render()
         if self._pipeline is not None:
-            return self._pipeline.step(actions)   # pinned host tensors, valid once the stream is synchronised
+            out = self._pipeline.step(actions)    # pinned host tensors
+            self._host_results_ready()
+            return out
         if self._fused:
             # action clamp, obs clamp and states clamp all happen inside the two fused launches
             _, rew, is_done, info = self._task.step(actions)
             obs = self._task._obs_bf16 if self._bf16 else self._task._obs_clipped
+            if getattr(self._task, "_host_io", False):
+                self._host_results_ready()        # the kernels wrote into pinned host memory: .to('cpu') below copies nothing
         else:
             obs, rew, is_done, info = self._task.step(torch.clamp(actions, -self._clip_actions, self._clip_actions))
             obs = torch.clamp(obs, -self._clip_obs, self._clip_obs)

@@ -59,6 +59,16 @@ def main():
         print(f"asym={asym} eager : obs {digest(env._obs_buf)} states {digest(env._states_buf)} reward {digest(env._reward_buf)}"
               f" terms {digest(env._term_rewards)} flags {digest(env._reset_buf, env._goal_reset_buf, env._successes, env._dones)}"
               f" stats {[round(float(x), 9) for x in env._step_stats.cpu()[:13]]}")
+        try:   # the wrapper's clamped copies (not part of -DLG_FAST_BUILD libraries)
+            from leibnizgym_b200.wrappers import VecTaskPython
+            vec = VecTaskPython(env, rl_device=dev, clip_obs=0.7, clip_actions=0.5)
+            for t in range(3, 5):
+                obs, rew, done, _ = vec.step(2.0 * ring.action[t])
+            torch.cuda.synchronize()
+            print(f"asym={asym} clip  : obs {digest(obs, env._obs_buf)} states {digest(vec.get_state(), env._states_buf)}"
+                  f" reward {digest(rew, done)} action {digest(env._action_buf, env._applied_torque)}")
+        except Exception as ex:  # noqa: BLE001
+            print(f"asym={asym} clip  : n/a ({type(ex).__name__})")
 
 
 if __name__ == "__main__":

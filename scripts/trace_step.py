@@ -26,15 +26,17 @@ from leibnizgym_b200.graph_runner import GraphRunner  # noqa: E402
 from leibnizgym_b200.sim import SyntheticSim  # noqa: E402
 from leibnizgym_b200.synthetic import bernoulli_masks, make_sequence  # noqa: E402
 
-SLOTS = 24
-POST = {0: "entry (w0)", 1: "after dependency wait", 2: "loads issued", 3: "staged (data arrived, w0)", 4: "after barrier",
+SLOTS = 32
+POST = {0: "entry (w0)", 1: "after dependency wait", 10: "loads issued, before trigger", 11: "windows stored (w0)",
+        22: "windows barrier passed", 2: "loads issued, after trigger", 23: "stats: ballots done", 24: "stats: lane sums done",
+        25: "stats: scaled (before atomic)", 3: "staged (data arrived, w0)", 4: "after barrier",
         5: "sub-task done (w0)", 16: "sub-task done (w1)", 17: "sub-task done (w2)", 18: "sub-task done (w3)",
         6: "after reward barrier", 7: "combined (w0)", 8: "statistics issued", 9: "emit done (w0)",
         19: "emit done (w1)", 20: "emit done (w2)", 21: "emit done (w3)",
         12: "entry (w4)", 13: "after dependency wait (w4)", 14: "after barrier (w4)", 15: "emit done (w4)"}
-PRE = {0: "entry", 1: "slabs issued", 2: "after dependency wait", 3: "flags + ballot", 4: "aggregate published",
-       5: "slabs landed", 6: "action row done", 7: "resets done", 8: "torque done", 9: "bulk stores issued",
-       10: "look-back + id lists done", 11: "exit"}
+PRE = {0: "entry", 1: "slabs issued", 2: "after dependency wait", 3: "aggregate published (scan group)",
+       4: "look-back + id lists done (scan group)", 5: "slabs landed", 6: "action row done", 7: "resets done",
+       8: "torque done", 9: "bulk stores issued", 11: "exit"}
 
 
 def read_trace(lib, which, ctas):
@@ -89,6 +91,8 @@ def main():
     pre_ctas = min(8192, (N + 127) // 128)
     tp, _ = read_trace(lib, 0, post_ctas)
     tp = tp[tp[:, 0] > 0]
+    for k in [k for k in POST if (tp[:, k] == 0).all()]:
+        POST.pop(k)    # points the traced kernel variant does not stamp
     if not a.post_only:
         tq, _ = read_trace(lib, 1, pre_ctas)
         tq = tq[tq[:, 0] > 0]

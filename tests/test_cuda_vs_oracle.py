@@ -83,7 +83,7 @@ def test_full_size_steps_match_oracle(difficulty, N, reset_p):
         _check("pre_sim_dof", env._dof_state, ora.sim.dof, w)
         info = {k_: float(v) for k_, v in env._step_info.items()}
         for k_, v in ora.step_info.items():
-            assert abs(info[k_] - float(v)) <= 1e-5 * abs(float(v)) + 2e-4, (w, k_, info[k_], float(v))
+            assert abs(info[k_] - float(v)) <= 1e-5 * abs(float(v)) + 1.35e-4, (w, k_, info[k_], float(v))   # tolerances.ATOL['terms']
 
 
 def test_sharding_is_invisible():

@@ -13,12 +13,19 @@ RTOL = 1e-5
 EXACT = {"reset_in", "goal_reset_in", "reset_ids", "goal_reset_ids", "dof_index_list", "root_index_list0",
          "root_index_list1", "root_index_list_move", "reset_buf", "goal_reset_buf", "steps_count", "successes", "sched_step"}
 
-# absolute floors
+# Absolute floors.  Each is at most 4x the largest error OBSERVED beyond the relative bound on the B200 over the three
+# BASELINE-size scenarios (tests/test_cuda_round2.py::test_observed_parity_errors_are_recorded re-measures them on every
+# GPU run, asserts exactly that, and leaves the numbers in gpurun_out/observed_parity_errors.json; round 2:
+# obs / states 8.9e-8 absolute and 3.3e-7 relative, i.e. nothing beyond the relative bound; torques and reset joint
+# rows bit-identical; goal poses 2.2e-8; terms 4.3e-5 and reward 3.6e-5 beyond the relative bound).
+# Where the term floor comes from: finger_reach_object_rate is weight x sum of six DIFFERENCES of 2-norms of ~0.1-0.6 m
+# (rewards.py:219-235), near zero while each norm carries up to one ulp (2^-24 x 0.5 m = 3e-8) of legitimate
+# evaluation-order difference: |weight| 750 x 2 ulps = 4.5e-5 is what is seen, 3 ulps (1.35e-4) what is allowed.
 ATOL = {
     "obs": 1e-6, "states": 1e-6, "action_buf": 0.0, "applied_torque": 1e-7,
     "goal_pose": 1e-7, "goal_movement": 1e-7,
     "pre_sim_dof": 1e-7, "pre_sim_obj_root": 1e-7, "pre_sim_goal_root": 1e-7,
-    "terms": 2e-4, "reward": 5e-4,
+    "terms": 1.35e-4, "reward": 1.35e-4,
 }
 
 
