@@ -291,7 +291,7 @@ def make_config(wl: dict, world: int, ring: int, ring_mib: float) -> dict:
 
 
 def ring_mib_of(envs: int, ring: int) -> float:
-    return ring * envs * 1724 / 2**20   # 18+52+260+9+18+9 floats of simulator state and action per env and slot
+    return ring * envs * 1464 / 2**20   # 18+52+260+9+18+9 floats of simulator state and action per env and slot
 
 
 def run_reference(args, wl):
@@ -458,6 +458,23 @@ def measure_device(args, wl, rank, world, local_rank, sampler=None):
         pre_graph = runner.capture(Ck, pre_only=True)
         pre_graph.replay()
         pre_ms = timer.run(pre_graph.replay, pre_graph.replay, min_ms=10.0, min_rep=9, max_rep=60)
+        # ---- what a plain device copy of the same number of bytes achieves at this size: R distinct source /
+        # destination buffers of half the post kernel's algorithmic bytes each (read + write = the same traffic),
+        # copied back to back from a graph like the kernels above.  The roofline peak is measured on a 4 GB copy; a
+        # 20 MB launch is in the launch-latency regime for a memcpy too, and this is the honest yardstick for it.
+        half = POST_BYTES[asym] * N // 2 // 4 * 4
+        src = torch.empty((R, half // 4), device=dev, dtype=torch.float32).normal_()
+        dst = torch.empty_like(src)
+        for t in range(2):
+            dst[t].copy_(src[t])
+        torch.cuda.synchronize()
+        copy_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(copy_graph):
+            for t in range(Ck):
+                dst[t % R].copy_(src[t % R])
+        copy_graph.replay()
+        copy_ms = timer.run(copy_graph.replay, copy_graph.replay, min_ms=10.0, min_rep=9, max_rep=60)
+        del src, dst
         if sampler is not None:
             sampler.stop()
         # ---- sharded statistics: the NCCL all-reduce against a gather + host sum of the same vectors ----------------
@@ -483,6 +500,7 @@ def measure_device(args, wl, rank, world, local_rank, sampler=None):
         cold_us_per_step=1e3 * cold_ms / K,
         post_us=1e3 * statistics.median(post_ms) / Ck, post_us_p10=1e3 * pctl(post_ms, 0.1) / Ck,
         post_us_p90=1e3 * pctl(post_ms, 0.9) / Ck, pre_us=1e3 * statistics.median(pre_ms) / Ck,
+        copy_us=1e3 * statistics.median(copy_ms) / Ck,
         value=float(K) * N * world / (med * 1e-3))
     return out
 
@@ -554,6 +572,8 @@ def run_gpu(args, wl):
                      "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,
                      "launch_us_p10": m["post_us_p10"], "launch_us_p90": m["post_us_p90"],
                      "pre_us": m["pre_us"], "pre_algorithmic_bytes_per_launch": PRE_BYTES * N,
+                     "device_copy_same_bytes_us": m["copy_us"],
+                     "device_copy_same_bytes_frac": post_bytes / (m["copy_us"] * 1e-6) / 1e9 / peak,
                      "step_us": m["us_per_step"], "whole_step_gbs": step_bytes / step_s / 1e9,
                      "whole_step_frac": step_bytes / step_s / 1e9 / peak},
         "clocks": clocks,

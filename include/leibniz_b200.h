@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LG_VERSION 100            /* 1.0.0 */
+#define LG_VERSION 110            /* 1.1.0 */
 #define LG_MAX_ACTION_DIM 18      /* position_impedance: 9 positions + 9 stiffnesses */
 #define LG_MAX_STATE_DIM 122      /* 50 + 6 + 39 + 9 + 18 */
 #define LG_NUM_TERMS 7            /* six reference terms + the keypoint extension */
@@ -216,9 +216,6 @@ typedef struct LgBuffers {
      caller does with `env._reset_buf |= mask` between steps (tests, reset-heavy workloads), without a separate pass */
   const uint8_t* force_reset;
   const uint8_t* force_goal_reset;
-  /* optional [LG_ROLE_TABLE_FLOATS] workspace filled once by lg_build_role_table: the per-lane set-up of
-     lg_post_physics (source, stride, output column, scale constants) as a table instead of per-launch branches */
-  const float* role_table;
 } LgBuffers;
 
 int lg_version(void);
@@ -231,11 +228,6 @@ size_t lg_struct_size(int which);
  * simulator rows, for which 32-byte fetches cut the DRAM over-fetch.  bytes in {32, 64, 128}. */
 int lg_set_l2_fetch_granularity(int bytes);
 
-/* Fills B->role_table (device, LG_ROLE_TABLE_FLOATS floats, 16-byte aligned) for the layout fields of P
- * (action_dim, asymmetric_obs, normalize_obs, actor / body strides and indices) and B->scale_table.  Call once per
- * env object, and again if one of those changes; lg_post_physics uses the table when the pointer is set. */
-#define LG_ROLE_TABLE_FLOATS 1024
-int lg_build_role_table(const LgParams* P, const LgBuffers* B, void* stream);
 
 /* number of look-back status words lg_pre_physics needs for n envs */
 int64_t lg_scan_tiles(int64_t num_envs);

@@ -25,7 +25,6 @@ LG_NUM_COEF = 20
 
 TERM_NAMES = ("finger_reach_object_rate", "finger_move_penalty", "object_dist", "object_rot",
               "object_rot_delta", "object_move", "keypoint")
-LG_ROLE_TABLE_FLOATS = 1024
 CMD_MODES = {"position": 0, "torque": 1, "position_impedance": 2}
 RESET_KINDS = {"none": 0, "default": 1, "random": 2}
 STAT_POSITION_GOAL, STAT_ORIENTATION_GOAL, STAT_SUCCESSES, STAT_REWARD, STAT_RESETS, STAT_DONES = 7, 8, 9, 10, 11, 12
@@ -86,7 +85,7 @@ class LgBuffers(C.Structure):
         "term_rewards", "step_stats", "reset_ids", "goal_reset_ids", "counts",
         "robot_indices", "reset_root_indices", "goal_root_indices", "scan_status", "control", "reward_coef", "scale_table",
         "inject_reset_u", "inject_reset_n", "inject_goal_u", "inject_goal_n", "obs_bf16", "states_bf16",
-        "force_reset", "force_goal_reset", "role_table")]
+        "force_reset", "force_goal_reset")]
 
 
 class LgHostStep(C.Structure):
@@ -105,7 +104,6 @@ SYMBOLS = {
     "lg_scan_tiles": (_i64, [_i64]),
     "lg_pre_resident_tiles": (_i64, []),
     "lg_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
-    "lg_build_role_table": (C.c_int, [_P, _B, _vp]),
     "lg_pre_physics": (C.c_int, [_P, _S, _B, _vp, _vp]),
     "lg_post_physics": (C.c_int, [_P, _S, _B, C.c_double, _vp]),
     "lg_fill_observations": (C.c_int, [_P, _S, _B, _vp]),

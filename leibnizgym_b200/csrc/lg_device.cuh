@@ -58,7 +58,11 @@ __device__ __forceinline__ float4 ld_hist4(const float4* p) {
 // the kernel runs.
 __device__ __forceinline__ float ld_stream1(const float* p) {
   float v;
+#ifdef LG_NC_LOADS
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#else
   asm volatile("ld.global.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#endif
   return v;
 }
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {

@@ -211,23 +211,13 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
   cudaError_t err;
   // rarely-used paths (DR noise, keypoint term, moving goal, bf16 copies) live in their own instantiation: switched off they cost nothing
   const bool ext = P->dr_activate || P->goal_rotation || ((P->term_active_mask >> LG_TERM_KEYPOINT) & 1) || B->obs_bf16 || B->states_bf16;
-  // The role set-up comes from the table lg_build_role_table filled when the caller provides one and the shard needs
-  // more than one wave: measured (us, post kernel alone) 262 144 envs 78.6 with the table vs 81.5 without; one-wave
-  // shards gain nothing (16 384 envs: 7.07 vs 7.10, whole step 11.39 vs 11.30 — the table fetch then sits in front of
-  // the tile's loads) and keep the in-kernel set-up, as does the stand-alone observation fill.  LG_ROLE_TABLE=0/1/2:
-  // never / multi-wave only (default) / always.
-  static const int table_mode = env_int("LG_ROLE_TABLE", 1);
-  const bool table = REWARD && B->role_table != nullptr &&
-                     (table_mode == 2 || (table_mode == 1 && (int64_t)grid > (int64_t)sm_count() * 4));
-  if (table && !aligned16(B->role_table)) return fail(LG_ERR_BAD_ARG, "role_table must be 16-byte aligned");
-#define LG_X(AD, AS, CL, EE, EX, TB) launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, EX, REWARD && TB>, grid, lg::kPostThreads, st, *P, *S, *B, cf)
+#define LG_X(AD, AS, CL, EE, EX) launch_pdl(pdl_mode() & 2, lg::post_physics_kernel<AD, AS, REWARD, CL, EE, EX>, grid, lg::kPostThreads, st, *P, *S, *B, cf)
 #ifdef LG_FAST_BUILD
-  if (ext || clip || table || P->action_dim != 9) return fail(LG_ERR_UNSUPPORTED, "LG_FAST_BUILD: instantiation not built");
-  if (asym) err = E == 28 ? LG_X(9, true, false, 28, false, false) : LG_X(9, true, false, 32, false, false);
-  else err = E == 28 ? LG_X(9, false, false, 28, false, false) : LG_X(9, false, false, 32, false, false);
+  if (ext || clip || P->action_dim != 9) return fail(LG_ERR_UNSUPPORTED, "LG_FAST_BUILD: instantiation not built");
+  if (asym) err = E == 28 ? LG_X(9, true, false, 28, false) : LG_X(9, true, false, 32, false);
+  else err = E == 28 ? LG_X(9, false, false, 28, false) : LG_X(9, false, false, 32, false);
 #else
-#define LG_T(AD, AS, CL, EE, EX) (table ? LG_X(AD, AS, CL, EE, EX, true) : LG_X(AD, AS, CL, EE, EX, false))
-#define LG_K(AD, AS, CL, EE) (ext ? LG_T(AD, AS, CL, EE, true) : LG_T(AD, AS, CL, EE, false))
+#define LG_K(AD, AS, CL, EE) (ext ? LG_X(AD, AS, CL, EE, true) : LG_X(AD, AS, CL, EE, false))
 #define LG_E(AD, AS, CL) (E == 16 ? LG_K(AD, AS, CL, 16) : E == 24 ? LG_K(AD, AS, CL, 24) : E == 28 ? LG_K(AD, AS, CL, 28) : LG_K(AD, AS, CL, 32))
   if (P->action_dim == 9) {
     if (asym) err = clip ? LG_E(9, true, true) : LG_E(9, true, false);
@@ -240,7 +230,6 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
 #ifndef LG_FAST_BUILD
 #undef LG_E
 #undef LG_K
-#undef LG_T
 #endif
 #undef LG_X
   if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("post_physics_kernel: ") + cudaGetErrorString(err));
@@ -270,9 +259,10 @@ size_t lg_struct_size(int which) {
 }
 int64_t lg_scan_tiles(int64_t n) { return (n + lg::kPreTile - 1) / lg::kPreTile; }
 int64_t lg_pre_resident_tiles(void) {
+  // the instantiation grids beyond one wave use (see pre_physics_kernel: MINB = 4)
   int per_sm9 = 0, per_sm18 = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, lg::pre_physics_kernel<9, false>, lg::kPreThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm18, lg::pre_physics_kernel<18, false>, lg::kPreThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, lg::pre_physics_kernel<9, false, 4>, lg::kPreThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm18, lg::pre_physics_kernel<18, false, 4>, lg::kPreThreads, 0);
   const int per_sm = per_sm9 < per_sm18 ? per_sm9 : per_sm18;
   cudaGetLastError();   // no device: report one CTA per SM of the default count rather than an error
   return (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
@@ -289,25 +279,6 @@ int lg_init_history(const LgParams* P, const LgSimState* S, const LgBuffers* B, 
   const int64_t total = P->num_envs * LG_HISTORY_COLS;
   lg::init_history_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*P, *S, *B);
   return check_launch("init_history_kernel");
-}
-
-int lg_build_role_table(const LgParams* P, const LgBuffers* B, void* stream) {
-  if (!P || !B || !B->role_table) return fail(LG_ERR_BAD_ARG, "null argument / role_table");
-  if (P->action_dim != 9 && P->action_dim != 18) return fail(LG_ERR_BAD_ARG, "action_dim must be 9 or 18");
-  if (P->normalize_obs && !B->scale_table) return fail(LG_ERR_BAD_ARG, "null scale_table");
-  if (!aligned16(B->role_table)) return fail(LG_ERR_BAD_ARG, "role_table must be 16-byte aligned");
-  static_assert(128 * lg::kRoleEntryFloats <= LG_ROLE_TABLE_FLOATS, "role table workspace too small");
-  float* table = const_cast<float*>(B->role_table);
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool asym = P->asymmetric_obs != 0;
-  if (P->action_dim == 9) {
-    if (asym) lg::build_role_table_kernel<9, true><<<1, 128, 0, st>>>(*P, B->scale_table, table);
-    else lg::build_role_table_kernel<9, false><<<1, 128, 0, st>>>(*P, B->scale_table, table);
-  } else {
-    if (asym) lg::build_role_table_kernel<18, true><<<1, 128, 0, st>>>(*P, B->scale_table, table);
-    else lg::build_role_table_kernel<18, false><<<1, 128, 0, st>>>(*P, B->scale_table, table);
-  }
-  return check_launch("build_role_table_kernel");
 }
 
 int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in, void* stream) {
@@ -328,9 +299,14 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
   static const bool force_ticket = env_flag("LG_PRE_TICKET");
   const bool ticket = force_ticket || tiles > resident_ctas;
 cudaError_t err;
-#define LG_PRE(AD, TK) err = launch_pdl(pdl_mode() & 1, lg::pre_physics_kernel<AD, TK>, (unsigned)tiles, lg::kPreThreads, st, *P, *S, *B, action_in, tiles)
-  if (P->action_dim == 9) { if (ticket) LG_PRE(9, true); else LG_PRE(9, false); }
-  else { if (ticket) LG_PRE(18, true); else LG_PRE(18, false); }
+  // one-wave grids (<= 3 CTAs per SM at 80 registers) run the latency-tuned instantiation, larger ones the 64-register one
+  const bool small = tiles <= 3 * sm_count();
+#define LG_PRE(AD, TK, MB) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB>, (unsigned)tiles, lg::kPreThreads, st, *P, *S, *B, action_in, tiles)
+  if (P->action_dim == 9) {
+    if (small && !ticket) LG_PRE(9, false, 1); else if (ticket) LG_PRE(9, true, 4); else LG_PRE(9, false, 4);
+  } else {
+    if (small && !ticket) LG_PRE(18, false, 1); else if (ticket) LG_PRE(18, true, 4); else LG_PRE(18, false, 4);
+  }
   if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("pre_physics_kernel: ") + cudaGetErrorString(err));
 #undef LG_PRE
   return check_launch("pre_physics_kernel");

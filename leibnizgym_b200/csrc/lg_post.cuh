@@ -135,22 +135,14 @@ __device__ __forceinline__ uint16_t to_bf16(float x) { return __bfloat16_as_usho
 // read from seven different tensors — and free of index arithmetic:
 //     load   v[k] = src[k * stride]                       (all loads of the tile in flight at once)
 //     emit   states[k][dcol] = obs[k][dcol] = scale(v[k])  (compile-time row offsets)
-// Role order puts what the reward terms read FIRST: object pose (7), goal pose (7) and the nine fingertip POSITION
-// columns are roles 0..22, i.e. all in warp 0 of a part (the "critical" warp).  Those lanes issue their loads before
-// any other lane does, so the 23 staged columns (and the previous history entry) are the first bytes DRAM returns and
-// the reward chain — the longest dependent chain of the kernel — starts while the bulk of the tile is still arriving.
-// Then: last action, joint state, and (asymmetric) the rest of the fingertip states, object velocity, wrenches and
-// joint torques.  The lanes that feed obs, the reward staging and the next history entry are all in the first two
-// warps of a part (`FRONT`); the other warps skip that code.
+// Role order = output column order of the states row, except that the nine fingertip POSITION columns
+// come right after the observation columns: the lanes that feed obs, the reward staging and the next
+// history entry are then all in the first two warps of a part, and the other warps skip that code.
 template <int A, bool ASYM, int E>
 struct Roles {
   static constexpr int OBS = 32 + A;
-  static constexpr int R_OBJ = 0;                       // 7 roles
-  static constexpr int R_GOAL = R_OBJ + 7;              // 7
-  static constexpr int R_TIPPOS = R_GOAL + 7;           // 9
-  static constexpr int R_ACT = R_TIPPOS + 9;            // A
-  static constexpr int R_DOF = R_ACT + A;               // 18
-  static constexpr int R_TIPREST = R_DOF + 18;          // 30 roles (asymmetric only)
+  static constexpr int R_TIPPOS = OBS;                  // 9 roles
+  static constexpr int R_TIPREST = R_TIPPOS + 9;        // 30 roles (asymmetric only)
   static constexpr int R_OBJVEL = R_TIPREST + 30;       // 6
   static constexpr int R_FT = R_OBJVEL + 6;             // 18
   static constexpr int R_TQ = R_FT + 18;                // 9
@@ -158,14 +150,12 @@ struct Roles {
   static constexpr int LANES = R_END <= 64 ? 64 : 128;  // role lanes per tile part
   static constexpr int PARTS = kPostThreads / LANES;    // the tile's envs are split over the parts
   static constexpr int EP = E / PARTS;                  // envs per lane
-  static constexpr int EP0 = EP;                        // envs of part 0 (an uneven 12 + 16 split measured the same)
   static_assert(E % PARTS == 0 && E <= 32, "tile must split evenly; the reward math uses one lane per env");
   static constexpr int FRONT = R_TIPREST;               // roles < FRONT may feed obs / staging / history
-  static constexpr int CRITICAL = R_ACT;                // roles < CRITICAL are staged for the reward terms
-  static_assert(CRITICAL <= 32, "the staged columns must sit in warp 0 of a part");
+  static constexpr int FRONT_WARPS = (FRONT + 31) / 32; // warps of a part that hold such roles
+  // warps that meet at the staging barrier: the four reward warps and the front warps of every part
+  static constexpr int STAGE_WARPS = LANES == 128 ? 4 + (PARTS - 1) * FRONT_WARPS : kPostThreads / 32;
   static_assert(R_END <= LANES, "more output columns than role lanes");
-  // warps that meet at the staging barrier: the four reward warps and warp 0 of every part
-  static constexpr int STAGE_WARPS = 4 + (LANES == 128 ? 1 : 2);   // {0,1,2,3,4} or {0,1,2,3,4,6}
 };
 
 // What a role lane needs to know, independent of the tile: where its column comes from, where it goes, and whether
@@ -192,29 +182,28 @@ __device__ __forceinline__ RoleInfo role_info(const LgParams& P, int role) {
     const int body = tip == 0 ? P.fingertip_body[0] : tip == 1 ? P.fingertip_body[1] : P.fingertip_body[2];
     return body * 13 + c;
   };
-  if (role < R::R_GOAL) {                                  // object pose (root row of actor 4e+2)  trifinger_env.py:975, :1011
-    const int c = role - R::R_OBJ;
+  if (role < 18) {                                         // dof_state (pos, vel) interleaved  trifinger_env.py:1003-1007
+    r.src_id = 0; r.src_off = role; r.stride = 18;
+    r.dcol = (role & 1) * 9 + (role >> 1);
+  } else if (role < 25) {                                  // object pose (root row of actor 4e+2)  :975, :1011
+    const int c = role - 18;
     r.src_id = 1; r.src_off = P.object_slot * 13 + c; r.stride = actor_stride;
     r.dcol = L::OFF_OBJ + c;
     r.stage_id = 1; r.stage_off = c; r.stage_stride = 7; r.hist_col = 9 + c;
-  } else if (role < R::R_TIPPOS) {                         // goal pose buffer                  :1015
-    const int c = role - R::R_GOAL;
+  } else if (role < 32) {                                  // goal pose buffer                  :1015
+    const int c = role - 25;
     r.src_id = 2; r.src_off = c; r.stride = 7;
     r.dcol = L::OFF_GOAL + c;
     r.stage_id = 2; r.stage_off = c; r.stage_stride = 7;
-  } else if (role < R::R_ACT) {                            // fingertip positions (bodies 6/11/16)  :974, :1040
+  } else if (role < R::OBS) {                              // last action                       :1019
+    const int c = role - 32;
+    r.src_id = 3; r.src_off = c; r.stride = A;
+    r.dcol = L::OFF_ACT + c;
+  } else if (role < R::R_TIPREST) {                        // fingertip positions (bodies 6/11/16)  :974, :1040
     const int j = role - R::R_TIPPOS, tip = j / 3, c = j - tip * 3;
     r.src_id = 4; r.src_off = tip_off(tip, c); r.stride = body_stride;
     r.dcol = ASYM ? L::OFF_TIPS + tip * 13 + c : -1;
     r.stage_id = 3; r.stage_off = j; r.stage_stride = 9; r.hist_col = j;
-  } else if (role < R::R_DOF) {                            // last action                       :1019
-    const int c = role - R::R_ACT;
-    r.src_id = 3; r.src_off = c; r.stride = A;
-    r.dcol = L::OFF_ACT + c;
-  } else if (role < R::R_TIPREST) {                        // dof_state (pos, vel) interleaved  :1003-1007
-    const int c = role - R::R_DOF;
-    r.src_id = 0; r.src_off = c; r.stride = 18;
-    r.dcol = (c & 1) * 9 + (c >> 1);
   } else if (role < R::R_OBJVEL) {                         // fingertip orientation + velocity
     const int j = role - R::R_TIPREST, tip = j / 10, c = 3 + (j - tip * 10);
     r.src_id = 4; r.src_off = tip_off(tip, c); r.stride = body_stride;
@@ -233,34 +222,6 @@ __device__ __forceinline__ RoleInfo role_info(const LgParams& P, int role) {
     r.dcol = L::OFF_TORQUE + c;
   }
   return r;
-}
-
-// The role set-up is ~150 instructions of branches per thread — a sixth of the kernel — and depends on nothing but
-// the simulator layout.  lg_build_role_table evaluates it once per env object into a 32-byte entry per role lane
-// (this kernel), and the TABLE instantiation of the post-physics kernel reads its entry with two 16-byte loads that
-// sit before the dependency wait.  Entry: int4 {src_id | stage_id<<4 | stage_stride<<8 | (hist_col+1)<<16, src_off,
-// stride, dcol}, float4 {centre, span/2, 2/span, stage_off (bits)}.
-constexpr int kRoleEntryFloats = 8;
-template <int A, bool ASYM>
-__global__ void build_role_table_kernel(const __grid_constant__ LgParams P, const float* __restrict__ scale_table,
-                                        float* __restrict__ table) {
-  using R = Roles<A, ASYM, 32>;
-  const int lane = threadIdx.x;
-  if (lane >= R::LANES) return;
-  int role = lane;
-  if (role >= R::R_END) role -= (R::LANES - R::R_END);
-  const RoleInfo r = role_info<A, ASYM>(P, role);
-  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
-  if (P.normalize_obs && r.dcol >= 0) {
-    centre = scale_table[r.dcol];
-    half_span = 0.5f * scale_table[LG_MAX_STATE_DIM + r.dcol];
-    rcp_half = 2.0f * scale_table[2 * LG_MAX_STATE_DIM + r.dcol];
-  }
-  int4 a;
-  a.x = r.src_id | (r.stage_id << 4) | (r.stage_stride << 8) | ((r.hist_col + 1) << 16);
-  a.y = r.src_off; a.z = r.stride; a.w = r.dcol;
-  reinterpret_cast<int4*>(table)[2 * lane] = a;
-  reinterpret_cast<float4*>(table)[2 * lane + 1] = make_float4(centre, half_span, rcp_half, __int_as_float(r.stage_off));
 }
 
 // Statistics in fixed point (see reward_combine): scale 2^30, values must stay below 2^28 so that 32 of them fit int64.
@@ -541,7 +502,7 @@ __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffer
   }
 }
 
-template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT, bool TABLE>
+template <int A, bool ASYM, bool REWARD, bool CLIP, int E, bool EXT>
 __global__ void __launch_bounds__(kPostThreads, 4)
 post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                     const __grid_constant__ LgBuffers B, const __grid_constant__ LgCoef CF) {
@@ -580,18 +541,9 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
   float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
   {
-    int src_id, src_off, stage_id, stage_off;
-    if constexpr (TABLE) {
-      const int4 a = __ldg(reinterpret_cast<const int4*>(B.role_table) + 2 * (tid % R::LANES));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(B.role_table) + 2 * (tid % R::LANES) + 1);
-      src_id = a.x & 15; stage_id = (a.x >> 4) & 15; stage_stride = (a.x >> 8) & 255; hist_col = ((a.x >> 16) & 255) - 1;
-      src_off = a.y; stride = a.z; dcol = a.w;
-      centre = b.x; half_span = b.y; rcp_half = b.z; stage_off = __float_as_int(b.w);
-    } else {
-      const RoleInfo r = role_info<A, ASYM>(P, role);
-      src_id = r.src_id; src_off = r.src_off; stride = r.stride; dcol = r.dcol;
-      stage_id = r.stage_id; stage_off = r.stage_off; stage_stride = r.stage_stride; hist_col = r.hist_col;
-    }
+    const RoleInfo r = role_info<A, ASYM>(P, role);
+    const int src_id = r.src_id, src_off = r.src_off, stage_id = r.stage_id, stage_off = r.stage_off;
+    stride = r.stride; dcol = r.dcol; stage_stride = r.stage_stride; hist_col = r.hist_col;
     const float* base = src_id == 0 ? S.dof_state : src_id == 1 ? S.root_state : src_id == 2 ? B.goal_pose
                       : src_id == 3 ? B.action : src_id == 4 ? S.rigid_body : src_id == 5 ? S.ft_sensors : S.dof_force;
     src = base + src_off;
@@ -615,7 +567,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   const uint8_t* p_reset = B.reset + e0 + renv;
   const int64_t* p_steps = B.steps_count + e0 + renv;
   asm volatile("" : "+l"(hist_src), "+l"(p_goal_reset), "+l"(p_succ), "+l"(p_reset), "+l"(p_steps), "+l"(src));
-  if (!TABLE && P.normalize_obs && dcol >= 0) {
+  if (P.normalize_obs && dcol >= 0) {
     centre = __ldg(B.scale_table + dcol);
     half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
     rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
@@ -632,11 +584,6 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     hprev = ld_hist4(hist_src);
     if (rw == 0) { in_goal_reset = *p_goal_reset; in_succ = *p_succ; in_reset = *p_reset; in_steps = *p_steps; }
   }
-  // The critical warp of every part (roles < CRITICAL: object pose, goal pose, fingertip positions) issues its
-  // loads before the other warps issue theirs: with the history pieces above these are the first requests in every
-  // memory queue, so the reward chain's inputs are the first bytes that come back.
-  const bool critical = (tid % R::LANES) < 32;
-  if (REWARD && !critical) asm volatile("bar.sync 2, %0;" :: "n"(kPostThreads) : "memory");
   float v[EP];
   if (full) {
 #pragma unroll
@@ -645,7 +592,6 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < EP; ++k) v[k] = k < cnt ? ld_stream1(src + (int64_t)k * stride) : 0.0f;
   }
-  if (REWARD && critical) asm volatile("bar.arrive 2, %0;" :: "n"(kPostThreads) : "memory");
   pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
   LG_TP(0, 2, tid == 0);
 
@@ -698,11 +644,12 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     }
   }
   LG_TP(0, 3, tid == 0);
-  // Staging barrier: the reward warps wait for the critical warps' staged columns (and the critical warps, which
-  // write the next history entry below, for the reward warps' reads of the previous one).  The other warps hold
-  // nothing anyone waits for: they go straight on to scale and store their columns as their data arrives.
+  // Staging barrier: the reward warps wait for the front warps' staged columns (and the front warps, which write
+  // the next history entry below, for the reward warps' reads of the previous one).  The other warps hold nothing
+  // anyone waits for: they go straight on to scale and store their columns as their data arrives.
   if (EXT || !REWARD) __syncthreads();   // extension: the noise tile is read by every observation lane
-  else if (rw < 4 || critical) asm volatile("bar.sync 3, %0;" :: "n"(R::STAGE_WARPS * 32) : "memory");
+  else if (R::STAGE_WARPS * 32 == kPostThreads) __syncthreads();
+  else if (rw < 4 || front) asm volatile("bar.sync 3, %0;" :: "n"(R::STAGE_WARPS * 32) : "memory");
   LG_TP(0, 4, tid == 0); LG_TP(0, 14, tid == 128);
 
   // ---- phase 3 (all warps; the reward warps come back to it after their math): scale and store the columns -----
@@ -775,8 +722,8 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
     // moving goal (__update_goal_movement_post, trifinger_env.py:1279-1284): after the rewards, the goal pose
     // buffer takes the pose the simulator integrated for the goal body.  The goal-role lanes own their elements
     // of goal_pose (read above, overwritten here), so no other lane observes the change within this step.
-    if (EXT && REWARD && P.goal_rotation && front && role >= R::R_GOAL && role < R::R_TIPPOS) {
-      const int c = role - R::R_GOAL, actor_stride = P.actors_per_env * 13;
+    if (EXT && REWARD && P.goal_rotation && front && role >= 25 && role < 32) {
+      const int c = role - 25, actor_stride = P.actors_per_env * 13;
       const float* g_src = S.root_state + ((e0 + env_first) * P.actors_per_env + P.goal_slot) * 13 + c;
       float* g_dst = B.goal_pose + (e0 + env_first) * 7 + c;
 #pragma unroll

@@ -141,8 +141,11 @@ __device__ __noinline__ void action_noise(const LgParams& P, uint64_t genv, uint
 // They meet for the resets (block-uniform branch: eight reset sub-tasks over the eight warps, lane = listed env);
 // the row group then computes the torque from the shared-memory slabs while the scan group resolves its look-back;
 // action and torque rows leave as bulk stores.
-template <int A, bool TICKET>
-__global__ void __launch_bounds__(kPreThreads)
+// MINB = CTAs per SM the register allocation must allow: 1 (80 registers, 3 CTAs per SM) for grids of one wave, where
+// the kernel is a latency chain (30 % resets at 16 384 envs: 17.3 against 18.0 us/step), 4 (64 registers) for larger
+// grids, where more rows in flight per SM is what counts (65 536 envs with goal resampling: 37.7 against 42.3 us/step).
+template <int A, bool TICKET, int MINB>
+__global__ void __launch_bounds__(kPreThreads, MINB)
 pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                    const __grid_constant__ LgBuffers B,
                    const float* __restrict__ action_in, int num_tiles) {

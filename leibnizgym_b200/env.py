@@ -313,8 +313,6 @@ class TrifingerEnv(IsaacEnvBase):
         tab[3] = self._P.dr_sigma
         tab[1][tab[1] == 0] = 1.0
         self._scale_table = torch.as_tensor(tab, device=dev).contiguous()
-        self._role_table = torch.zeros(nat.LG_ROLE_TABLE_FLOATS, device=dev, dtype=torch.float)
-        self._role_table_ready = False
 
     def _configure_mdp_spaces(self):
         """Scale vectors as tensors, for callers that read them (ref trifinger_env.py:630-748)."""
@@ -352,7 +350,6 @@ class TrifingerEnv(IsaacEnvBase):
         b.obs_bf16, b.states_bf16 = p(self._obs_bf16), p(self._states_bf16)
         fr, fg = getattr(self, "_force_masks", (None, None))
         b.force_reset, b.force_goal_reset = p(fr), p(fg)
-        b.role_table = p(self._role_table)
         b.reset_ids, b.goal_reset_ids, b.counts = p(self._reset_ids), p(self._goal_reset_ids), p(self._counts)
         b.robot_indices, b.reset_root_indices, b.goal_root_indices = p(self._robot_indices), p(self._reset_root_indices), p(self._goal_root_indices)
         b.scan_status, b.control = p(self._scan_status), p(self._control)
@@ -362,12 +359,6 @@ class TrifingerEnv(IsaacEnvBase):
         if not getattr(self, "_history_seeded", False):
             self._call("lg_init_history", self._P, self._S, self._B)  # ref trifinger_env.py:619-628
             self._history_seeded = True
-        if not self._role_table_ready and os.environ.get("LG_NO_ROLE_TABLE") is None:
-            # the post-physics kernel's per-lane set-up, evaluated once (the layout fields of _P never change)
-            nat.check(self._lib.lg_build_role_table(self._P, self._B, self._stream()), "lg_build_role_table")
-            self._role_table_ready = True
-        if not self._role_table_ready:
-            self._B.role_table = None
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self._torch_device).cuda_stream

@@ -117,11 +117,47 @@ def copy_json(src_name, dst_name):
         open(os.path.join(PROF, dst_name), "w").write(line + "\n")
 
 
+def sass_histogram():
+    """Opcode histogram of the two step kernels of the shipped library (cuobjdump -sass): what the evidence table of
+    B200_PROFILING.md asks for (UBLKCP / SYNCS = bulk copies + mbarrier, ACQBULK / PREEXIT = programmatic dependent
+    launch, REDUX = warp-reduce unit; no UTC*MMA / LDTM: the path has no contraction)."""
+    so = os.path.join(ROOT, "leibnizgym_b200", "libleibniz_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    out, cur, hist = [], None, None
+    wanted = ("post_physics_kernelILi9ELb1ELb1ELb0ELi28ELb0ELb0E", "pre_physics_kernelILi9ELb0E")
+    for line in sass.splitlines():
+        if "Function :" in line:
+            if cur:
+                out.append((cur, hist))
+            name = line.split("Function :")[1].strip()
+            cur, hist = (name, collections.Counter()) if any(w in name for w in wanted) else (None, None)
+        elif cur and "/*" in line and ";" in line:
+            body = line.split("*/", 1)[1].strip()
+            if body.startswith("/*"):
+                continue
+            tok = body.split()
+            op = tok[1] if tok[0].startswith("@") and len(tok) > 1 else tok[0]
+            hist[op.rstrip(";")] += 1
+    if cur:
+        out.append((cur, hist))
+    with open(os.path.join(PROF, f"{R}_sass_opcodes.txt"), "w") as f:
+        f.write("cuobjdump -sass leibnizgym_b200/libleibniz_b200.so (sm_100a): static opcode counts of the two step kernels\n")
+        for name, h in out:
+            total = sum(h.values())
+            f.write(f"\n{name}: {total} instructions\n")
+            key = [k for k in h if any(t in k for t in ("UBLKCP", "SYNCS", "ACQBULK", "PREEXIT", "REDUX", "LDG", "STG", "RED", "ATOM",
+                                                         "BAR", "MUFU", "DADD", "DMUL", "DFMA", "F2F", "SHFL", "LDS", "STS", "UTC", "LDTM", "HMMA"))]
+            f.write("  marker opcodes: " + ", ".join(f"{k} x{h[k]}" for k in sorted(key)) + "\n")
+            f.write("  top 25: " + ", ".join(f"{k} x{v}" for k, v in h.most_common(25)) + "\n")
+
+
 if __name__ == "__main__":
+    sass_histogram()
     launch_list()
     full_metrics(os.path.join(OUT, f"prof_{R}.ncu-rep"), os.path.join(PROF, f"{R}_ncu_full_metrics.csv"), "post_physics_kernel")
     full_metrics(os.path.join(OUT, f"prof_big_{R}.ncu-rep"), os.path.join(PROF, f"{R}_ncu_full_metrics_262144envs.csv"))
     copy_json(f"bench_{R}.json", f"{R}_bench_c2_1gpu.json")
+    copy_json(f"bench_driver_{R}.json", f"{R}_bench_c2_1gpu_driver_flags.json")
     copy_json(f"bench_ref_{R}.json", f"{R}_bench_reference_arm.json")
     for wl in ("c2sym", "c2kp", "c3", "c3ref", "c3reset", "c4", "c5"):
         copy_json(f"bench_{wl}_{R}.json", f"{R}_bench_{wl}_1gpu.json")
@@ -130,6 +166,7 @@ if __name__ == "__main__":
     for g in (2, 4, 8):
         for wl in ("c2", "c4", "c5"):
             copy_json(f"bench_{wl}_{g}gpu_{R}.json", f"{R}_bench_{wl}_{g}gpu.json")
+        copy_json(f"bench_driver_{g}gpu_{R}.json", f"{R}_bench_c2_{g}gpu_driver_flags.json")
     smi = os.path.join(OUT, f"smi_{R}.csv")
     if os.path.exists(smi):
         shutil.copy(smi, os.path.join(PROF, f"{R}_nvidia_smi.csv"))

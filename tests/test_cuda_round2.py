@@ -1,5 +1,5 @@
 """GPU tests added in round 2: the ticket path of the fused pre-physics kernel at the largest advertised shard size,
-the simulator notifications of the fused step, the table-driven kernel variant against the in-kernel set-up, the blocking
+the simulator notifications of the fused step, the blocking
 host-output wrapper, and the observed-error report that the tolerance floors are derived from."""
 import json
 import os
@@ -23,7 +23,7 @@ def _check(key, got, exp, where, extra=None):
     assert ok, (where, key, detail)
 
 
-@pytest.mark.parametrize("N", [262_144, 60_001])
+@pytest.mark.parametrize("N", [262_144, 80_001])
 def test_ticket_path_full_step_matches_oracle(N):
     """`pre_physics_kernel<A, TICKET=true>` (grids larger than what is co-resident take their tiles by ticket,
     csrc/lg_kernels.cu lg_pre_physics) with 30 % resets + 5 % goal resets, success termination on: reset / goal-reset
@@ -162,24 +162,6 @@ def test_blocking_host_outputs_are_complete_on_return():
     for t, (a, b) in enumerate(zip(outs["cuda:0"], outs["cpu"])):
         for i, (x, y) in enumerate(zip(a, b)):
             assert torch.equal(x, y), (t, i)
-
-
-def test_role_table_kernel_equals_in_kernel_setup():
-    """The table-driven instantiation of the post-physics kernel (`LG_ROLE_TABLE=2`: role set-up read from the table
-    lg_build_role_table wrote) and the in-kernel set-up (`LG_ROLE_TABLE=0`) are two routes to the same per-lane
-    constants: every output buffer bit-identical over the fixed scenario of scripts/digest_step.py (20 000 envs, both
-    observation modes, 30 % resets + 5 % goal resets, graph replay and eager steps, the wrapper's clamped copies)."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = os.path.join(root, "scripts", "digest_step.py")
-    outs = []
-    for mode in ("2", "0"):
-        env = dict(os.environ, LG_ROLE_TABLE=mode)
-        res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
-        assert res.returncode == 0, res.stderr[-2000:]
-        outs.append(res.stdout)
-    assert outs[0] == outs[1] and "asym=False clip  : obs" in outs[0], (outs[0], outs[1])
 
 
 def test_observed_parity_errors_are_recorded():

@@ -135,30 +135,6 @@ def test_rl_games_adapter_shapes_without_a_gpu():
     assert asym.reset() is asym.full_state and asym.get_env_info()["state_space"] == "S"
 
 
-def test_simulator_control_plane_is_forwarded_or_refused():
-    """get/set_gravity live in the config; sim-parameter and camera calls go to the simulator object or raise
-    (ref env_base.py:175-220) — checked on the base class without constructing a CUDA env."""
-    from leibnizgym_b200.config import resolve_config
-    from leibnizgym_b200.env import IsaacEnvBase
-    env = IsaacEnvBase.__new__(IsaacEnvBase)
-    env.config = resolve_config({"num_instances": 4})
-
-    class Sim:
-        def set_sim_params(self, p):
-            self.p = p
-
-        def get_sim_params(self):
-            return self.p
-
-    env._sim = Sim()
-    env.set_gravity((0, 0, -1.5))
-    assert env.get_gravity().tolist() == [0.0, 0.0, -1.5]
-    env.set_sim_params({"dt": 0.01})
-    assert env.get_sim_params() == {"dt": 0.01}
-    with pytest.raises(NotImplementedError):
-        env.set_camera_lookat((1, 1, 1), (0, 0, 0))
-
-
 def test_every_bench_workload_resolves_to_kernel_parameters():
     """bench.py's workloads (SURVEY.md 8d C2-C5 and their variants) produce valid env configs and parameter blocks,
     with and without the extension features."""
