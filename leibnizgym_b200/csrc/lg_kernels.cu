@@ -261,8 +261,8 @@ int64_t lg_scan_tiles(int64_t n) { return (n + lg::kPreTile - 1) / lg::kPreTile;
 int64_t lg_pre_resident_tiles(void) {
   // the instantiation grids beyond one wave use (see pre_physics_kernel: MINB = 4)
   int per_sm9 = 0, per_sm18 = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, lg::pre_physics_kernel<9, false, 4>, lg::kPreThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm18, lg::pre_physics_kernel<18, false, 4>, lg::kPreThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm9, lg::pre_physics_kernel<9, false, 4, true>, lg::kPreThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm18, lg::pre_physics_kernel<18, false, 4, true>, lg::kPreThreads, 0);
   const int per_sm = per_sm9 < per_sm18 ? per_sm9 : per_sm18;
   cudaGetLastError();   // no device: report one CTA per SM of the default count rather than an error
   return (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
@@ -301,13 +301,13 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
 cudaError_t err;
   // one-wave grids (<= 3 CTAs per SM at 80 registers) run the latency-tuned instantiation, larger ones the 64-register one
   const bool small = tiles <= 3 * sm_count();
-#define LG_PRE(AD, TK, MB) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB>, (unsigned)tiles, lg::kPreThreads, st, *P, *S, *B, action_in, tiles)
+#define LG_PRE(AD, TK, MB, SP) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB, SP>, (unsigned)tiles, \
+                                              SP ? lg::kPreThreads : lg::kScanThreads, st, *P, *S, *B, action_in, tiles)
   if (P->action_dim == 9) {
-    if (small && !ticket) LG_PRE(9, false, 1); else if (ticket) LG_PRE(9, true, 4); else LG_PRE(9, false, 4);
+    if (ticket) LG_PRE(9, true, 6, false); else if (small) LG_PRE(9, false, 1, true); else LG_PRE(9, false, 4, true);
   } else {
-    if (small && !ticket) LG_PRE(18, false, 1); else if (ticket) LG_PRE(18, true, 4); else LG_PRE(18, false, 4);
+    if (ticket) LG_PRE(18, true, 6, false); else if (small) LG_PRE(18, false, 1, true); else LG_PRE(18, false, 4, true);
   }
-  if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("pre_physics_kernel: ") + cudaGetErrorString(err));
 #undef LG_PRE
   return check_launch("pre_physics_kernel");
 }

@@ -144,8 +144,13 @@ __device__ __noinline__ void action_noise(const LgParams& P, uint64_t genv, uint
 // MINB = CTAs per SM the register allocation must allow: 1 (80 registers, 3 CTAs per SM) for grids of one wave, where
 // the kernel is a latency chain (30 % resets at 16 384 envs: 17.3 against 18.0 us/step), 4 (64 registers) for larger
 // grids, where more rows in flight per SM is what counts (65 536 envs with goal resampling: 37.7 against 42.3 us/step).
-template <int A, bool TICKET, int MINB>
-__global__ void __launch_bounds__(kPreThreads, MINB)
+//
+// SPLIT = false is the same pass with ONE 128-thread group doing both chains one after the other (look-back last, when
+// every predecessor has long published): grids of many waves are bound by the rows in flight per SM, not by the length
+// of a CTA's chain, and half-idle CTAs of 256 threads cost them a third of their throughput (1 048 576 envs: 84 against
+// 54 us).  Used together with the ticket path.
+template <int A, bool TICKET, int MINB, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kPreThreads : kScanThreads, MINB)
 pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
                    const __grid_constant__ LgBuffers B,
                    const float* __restrict__ action_in, int num_tiles) {
@@ -160,8 +165,10 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   __shared__ uint32_t s_scan[4];           // tile totals (a, b) and the global exclusive prefix (a, b)
   __shared__ uint16_t s_reset_list[E], s_goal_list[E];
   const int tid = threadIdx.x;
+  constexpr int NT = SPLIT ? kPreThreads : kScanThreads;   // threads of the CTA
   const int gt = tid & (kScanThreads - 1);
-  const bool row_group = tid < kScanThreads;
+  const bool row_group = !SPLIT || tid < kScanThreads;
+  const bool scan_group = !SPLIT || tid >= kScanThreads;
   LG_TP(1, 0, tid == 0);
   // Launched programmatically after lg_post_physics (see pdl_mode): what this kernel reads before pdl_wait() below
   // must not be written by that kernel.  The control block (epoch, ticket) is only written by this kernel's own
@@ -210,7 +217,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   TileScan t;
   t.tile = tile; t.epoch = epoch;
   bool f_reset = false, f_goal = false;
-  if (!row_group) {
+  if (scan_group) {
     uint8_t flag_r = 0, flag_g = 0;
     if (live) {
       flag_r = B.reset[e]; flag_g = B.goal_reset[e];
@@ -237,7 +244,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
                  (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
       s_scan[0] = t.total_a; s_scan[1] = t.total_b;
     }
-    LG_TP(1, 3, tid == kScanThreads);
+    LG_TP(1, 3, tid == NT - kScanThreads);
   }
   __syncthreads();   // flags, tile totals and reset lists are visible to everyone; the mbarrier is initialised
   const int na = (int)s_scan[0], nb = (int)s_scan[1];
@@ -267,12 +274,12 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
       B.goal_reset_ids[j] = e;
       if (B.goal_root_indices) B.goal_root_indices[j] = (int32_t)(P.actors_per_env * e) + P.goal_slot;
     }
-    LG_TP(1, 4, tid == kScanThreads);
+    LG_TP(1, 4, tid == NT - kScanThreads);
   };
   if (rank_first) {
-    if (!row_group) finish_scan();
+    if (scan_group) finish_scan();
     __syncthreads();
-  } else if (!resets && !row_group) {
+  } else if (SPLIT && !resets && scan_group) {
     finish_scan();
   }
 
@@ -313,7 +320,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   // warps (lane = listed env): uniform control flow, and a serial chain of ~2 Philox blocks per warp instead of ten
   // per resetting thread.
   if (resets) {
-    if (full_tile && !row_group) mbar_wait(&s_mbar, 0);   // new joint rows are mirrored into the landed slab
+    if (full_tile && !row_group) mbar_wait(&s_mbar, 0);   // new joint rows are mirrored into the landed slab (the row group has waited)
     const uint32_t ex_a = s_scan[2], ex_b = s_scan[3];     // meaningful with injected draws only (rank_first)
     const int warp = tid >> 5, lane = tid & 31;
     auto run_sub = [&](int sub, int first, int step) {
@@ -328,11 +335,17 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     };
     // the two long sub-tasks (object pose: 2 Philox blocks, sqrt, 2 sincos; goal: 2-3 blocks, Box-Muller, normalise)
     // take two and three warps, the six short ones (joint blocks 0..4, bookkeeping) two each of the other three
-    if (warp < 2) run_sub(5, warp * 32 + lane, 64);
-    else if (warp < 5) run_sub(6, (warp - 2) * 32 + lane, 96);
-    else { run_sub(warp - 5, lane, 32); run_sub(warp == 7 ? 7 : warp - 2, lane, 32); }
+    if (SPLIT) {
+      if (warp < 2) run_sub(5, warp * 32 + lane, 64);
+      else if (warp < 5) run_sub(6, (warp - 2) * 32 + lane, 96);
+      else { run_sub(warp - 5, lane, 32); run_sub(warp == 7 ? 7 : warp - 2, lane, 32); }
+    } else {   // four warps: the long sub-tasks on two warps each, then the six short ones
+      run_sub(warp < 2 ? 5 : 6, tid & 63, 64);
+      run_sub(warp, lane, 32);                                   // joint blocks 0..3
+      if (warp < 2) run_sub(warp == 0 ? 4 : 7, lane, 32);        // joint block 4, bookkeeping
+    }
 #pragma unroll 1
-    for (int r = tid; r < nb; r += kPreThreads) {   // goal resets second, as in env_base.py:374-379
+    for (int r = tid; r < nb; r += NT) {   // goal resets second, as in env_base.py:374-379
       const int64_t env = e0 + s_goal_list[r];
       const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
                                        (int64_t)ex_b + r);
@@ -341,7 +354,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     }
     LG_TP(1, 7, tid == 0);
     __syncthreads();   // the mirrored joint rows are final before the torque reads them
-    if (!rank_first && !row_group) finish_scan();
+    if (SPLIT && !rank_first && scan_group) finish_scan();
   }
   // ---- moving goal (__update_goal_movement_pre, trifinger_env.py:1267-1277): every step the goal body's
   // angular velocity is re-imposed from the movement buffer (freshly sampled above for envs that reset)
@@ -371,10 +384,11 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
     }
   } else {
     __syncthreads();
-    for (int i = tid; i < nvalid * A; i += kPreThreads) B.action[e0 * A + i] = s_act[i];
+    for (int i = tid; i < nvalid * A; i += NT) B.action[e0 * A + i] = s_act[i];
     if (want_torque)
-      for (int i = tid; i < nvalid * 9; i += kPreThreads) B.applied_torque[e0 * 9 + i] = s_tq[i];
+      for (int i = tid; i < nvalid * 9; i += NT) B.applied_torque[e0 * 9 + i] = s_tq[i];
   }
+  if (!SPLIT && !rank_first) finish_scan();   // one group: the look-back and the id lists come last
   LG_TP(1, 11, tid == 0);
 }
 
