@@ -270,19 +270,16 @@ __device__ __forceinline__ Quat sample_orientation(const float n[4]) {
   return Quat{__fdiv_rn(n[0], den), __fdiv_rn(n[1], den), __fdiv_rn(n[2], den), __fdiv_rn(n[3], den)};
 }
 
-// __sample_object_goal_poses (envs/trifinger/trifinger_env.py:1194-1265; draw order SURVEY.md §A.5)
-__device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource& dr, const float ug[3], float pose[7],
-                                            float angvel[3]) {
+// __sample_object_goal_poses (envs/trifinger/trifinger_env.py:1194-1265; draw order SURVEY.md §A.5), in two halves
+// that share nothing — position (uniform columns 21..23) and orientation + angular velocity (the normals) — so that
+// the fused kernel can run them on different warps: together they are the longest dependent chain of a reset.
+__device__ __forceinline__ void sample_goal_position(const LgParams& P, const float ug[3], float pos[3]) {
   const int d = P.task_difficulty;
   float x = 0.0f, y = 0.0f, z;
-  Quat q{0.0f, 0.0f, 0.0f, 1.0f};
   const float half = (float)P.cube_half_size;
   if (d == -1 || d == 1 || d == 3 || d == 4 || d == 5)
     sample_disc(ug[0], ug[1], (float)P.max_com_distance, x, y);
-  if (d == -1) {
-    z = half;
-    q = sample_yaw(ug[2]);
-  } else if (d == 1) {
+  if (d == -1 || d == 1) {
     z = half;
   } else if (d == 3) {
     z = (float)(P.cube_max_height - P.cube_half_size) * ug[2] + half;
@@ -291,6 +288,13 @@ __device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource&
   } else {  // 2, 6: fixed position in the air
     z = (float)(P.cube_half_size + 0.05);
   }
+  pos[0] = x; pos[1] = y; pos[2] = z;
+}
+__device__ __forceinline__ void sample_goal_orientation(const LgParams& P, const DrawSource& dr, float yaw_u, float quat[4],
+                                                        float angvel[3]) {
+  const int d = P.task_difficulty;
+  Quat q{0.0f, 0.0f, 0.0f, 1.0f};
+  if (d == -1) q = sample_yaw(yaw_u);
   if (d == 4 || d == 5 || d == 6) {
     float n[4];
     dr.normal4(true, n);
@@ -306,38 +310,48 @@ __device__ __forceinline__ void sample_goal(const LgParams& P, const DrawSource&
     angvel[1] = mag * __fdiv_rn(n[1], len);
     angvel[2] = mag * __fdiv_rn(n[2], len);
   }
-  pose[0] = x; pose[1] = y; pose[2] = z;
-  pose[3] = q.x; pose[4] = q.y; pose[5] = q.z; pose[6] = q.w;
+  quat[0] = q.x; quat[1] = q.y; quat[2] = q.z; quat[3] = q.w;
 }
 
-// Writes the sampled goal into the goal buffers and the goal actor's root row
-// (trifinger_env.py:1248-1265).
+// Write the sampled goal into the goal buffers and the goal actor's root row (trifinger_env.py:1248-1265):
+// `half` 0 = position (+ the row's linear velocity), 1 = orientation and angular velocity, 2 = both.
 __device__ __noinline__ void apply_goal_sample(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                               int64_t e, const DrawSource& dr, const float* ub5 = nullptr) {
-  float pose[7], angvel[3], u5[4];
-  if (ub5) { u5[1] = ub5[1]; u5[2] = ub5[2]; u5[3] = ub5[3]; }
-  else dr.uniform4(5, u5);                      // goal columns 21..23 live in uniform block 5
-  sample_goal(P, dr, u5 + 1, pose, angvel);
+                                               int64_t e, const DrawSource& dr, int half = 2) {
   float* gp = B.goal_pose + e * 7;
   float* gm = B.goal_movement + e * 6;
   float* row = S.root_state + ((int64_t)P.actors_per_env * e + P.goal_slot) * 13;
+  // goal columns 21..23 live in uniform block 5; the yaw of difficulty -1 is its last column
+  float u5[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (half != 1 || P.task_difficulty == -1) dr.uniform4(5, u5);
+  if (half != 1) {
+    float pos[3];
+    sample_goal_position(P, u5 + 1, pos);
 #pragma unroll
-  for (int c = 0; c < 7; ++c) { gp[c] = pose[c]; row[c] = pose[c]; }
+    for (int c = 0; c < 3; ++c) { gp[c] = pos[c]; row[c] = pos[c]; row[7 + c] = gm[c]; }
+  }
+  if (half != 0) {
+    float quat[4], angvel[3];
+    sample_goal_orientation(P, dr, u5[3], quat, angvel);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { gm[3 + c] = angvel[c]; row[7 + c] = gm[c]; row[10 + c] = angvel[c]; }
+    for (int c = 0; c < 4; ++c) { gp[3 + c] = quat[c]; row[3 + c] = quat[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { gm[3 + c] = angvel[c]; row[10 + c] = angvel[c]; }
+  }
 }
 
-// _reset_impl for ONE env (trifinger_env.py:373-411, :1101-1192) cut into EIGHT independent sub-tasks, so that the
+// _reset_impl for ONE env (trifinger_env.py:373-411, :1101-1192) cut into TEN independent sub-tasks, so that the
 // fused kernel can run them on different warps (uniform control flow inside a warp) instead of one long serial
 // chain per resetting env.  The draws are counter-based (or injected by column), so every sub-task fetches exactly
 // the columns it needs; the arithmetic per output is unchanged.  Index lists are written by the caller.
 //   0..4  robot joint state, uniform block b = canonical columns 4b..4b+3 (pos 0..8 | vel 9..17)     :1119-1144
-//   5     object pose -> root row + history entry                                                      :1164-1192
-//   6     goal pose / movement (skipped when a goal reset of the same env follows and overwrites it)   :408-411
+//   5, 8  object position / orientation -> root row + history entry                                    :1164-1192
+//   6, 9  goal position / orientation + movement (skipped when a goal reset of the same env follows)   :408-411
 //   7     episode bookkeeping                                                                           :382-387
+// The four long ones (5, 8, 6, 9: a Philox block each, then sqrt / sincos, or Box-Muller and a normalisation) are halves
+// of what used to be two sub-tasks: the goal pose alone was a chain of ~550 instructions per resetting env.
 // The zeroing of fingertip history entry 1 (:1146-1147) is a dead write in the reference and has
 // no counterpart here.
-constexpr int kResetSubtasks = 8;
+constexpr int kResetSubtasks = 10;
 // `dof_mirror`: optional second destination of the env's new joint-state row (the fused kernel's shared-memory copy,
 // from which the torque is computed right afterwards).
 // Out of line on purpose: the fused kernel reaches it from several call sites behind a block-uniform branch that most
@@ -366,29 +380,37 @@ __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& 
         if (dof_mirror) dof_mirror[2 * j + (is_vel ? 1 : 0)] = x;
       }
     }
-  } else if (sub == 5) {
+  } else if (sub == 5 || sub == 8) {
     // history entry 0 gets (pose, 0 velocity); its pose part is what the next post-physics pass reads as
-    // "previous object pose" 
+    // "previous object pose" (SURVEY.md §C2).  5: position (+ zero velocities), 8: orientation.
     if (P.object_reset == LG_RESET_NONE) return;
-    float x = 0.0f, y = 0.0f;
-    const float z = (float)P.cube_half_size;
-    Quat q{0.0f, 0.0f, 0.0f, 1.0f};
-    if (P.object_reset == LG_RESET_RANDOM) {
-      float ub4[4], ub5[4];
-      dr.uniform4(4, ub4);                       // columns 18, 19 (disc radius, angle) are lanes 2, 3
-      dr.uniform4(5, ub5);                       // column 20 (object yaw)
-      sample_disc(ub4[2], ub4[3], (float)P.max_com_distance, x, y);
-      q = sample_yaw(ub5[0]);
-    }
-    const float pose[7] = {x, y, z, q.x, q.y, q.z, q.w};
     float* h = B.history + e * LG_HISTORY_COLS + 9;
     float* row = S.root_state + ((int64_t)P.actors_per_env * e + P.object_slot) * 13;
+    if (sub == 5) {
+      float x = 0.0f, y = 0.0f;
+      const float z = (float)P.cube_half_size;
+      if (P.object_reset == LG_RESET_RANDOM) {
+        float ub4[4];
+        dr.uniform4(4, ub4);                     // columns 18, 19 (disc radius, angle) are lanes 2, 3
+        sample_disc(ub4[2], ub4[3], (float)P.max_com_distance, x, y);
+      }
+      h[0] = x; h[1] = y; h[2] = z;
+      row[0] = x; row[1] = y; row[2] = z;
 #pragma unroll
-    for (int c = 0; c < 7; ++c) { h[c] = pose[c]; row[c] = pose[c]; }
-#pragma unroll
-    for (int c = 7; c < 13; ++c) row[c] = 0.0f;
-  } else if (sub == 6) {
-    if (!goal_reset_follows) apply_goal_sample(P, S, B, e, dr);   // goal columns 21..23 live in uniform block 5
+      for (int c = 7; c < 13; ++c) row[c] = 0.0f;
+    } else {
+      Quat q{0.0f, 0.0f, 0.0f, 1.0f};
+      if (P.object_reset == LG_RESET_RANDOM) {
+        float ub5[4];
+        dr.uniform4(5, ub5);                     // column 20 (object yaw)
+        q = sample_yaw(ub5[0]);
+      }
+      h[3] = q.x; h[4] = q.y; h[5] = q.z; h[6] = q.w;
+      row[3] = q.x; row[4] = q.y; row[5] = q.z; row[6] = q.w;
+    }
+  } else if (sub == 6 || sub == 9) {
+    // 6: goal position, 9: goal orientation + angular velocity
+    if (!goal_reset_follows) apply_goal_sample(P, S, B, e, dr, sub == 6 ? 0 : 1);
   } else {
     B.reset[e] = 0;
     B.steps_count[e] = 0;
@@ -402,7 +424,8 @@ __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& 
 __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimState& S, const LgBuffers& B,
                                               int64_t e, const DrawSource& dr) {
   reset_subtask(P, S, B, e, 7, dr, false);
-  for (int sub = 0; sub < 7; ++sub) reset_subtask(P, S, B, e, sub, dr, false);
+  for (int sub = 0; sub < kResetSubtasks; ++sub)
+    if (sub != 7) reset_subtask(P, S, B, e, sub, dr, false);
 }
 
 // _pre_step for ONE env (trifinger_env.py:442-498): action -> applied joint torque

@@ -299,14 +299,22 @@ int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, c
   static const bool force_ticket = env_flag("LG_PRE_TICKET");
   const bool ticket = force_ticket || tiles > resident_ctas;
 cudaError_t err;
-  // one-wave grids (<= 3 CTAs per SM at 80 registers) run the latency-tuned instantiation, larger ones the 64-register one
-  const bool small = tiles <= 3 * sm_count();
+  // grids that are co-resident at 3 CTAs per SM (<= 85 registers) run the latency-tuned instantiation, larger ones
+  // the 64-register one; both thresholds come from the occupancy of the instantiation that is launched
+  static const int64_t resident_small = [] {
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, lg::pre_physics_kernel<9, false, 3, true>, lg::kPreThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, lg::pre_physics_kernel<18, false, 3, true>, lg::kPreThreads, 0);
+    const int per_sm = a < b ? a : b;
+    return (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
+  }();
+  const bool small = tiles <= resident_small;
 #define LG_PRE(AD, TK, MB, SP) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB, SP>, (unsigned)tiles, \
                                               SP ? lg::kPreThreads : lg::kScanThreads, st, *P, *S, *B, action_in, tiles)
   if (P->action_dim == 9) {
-    if (ticket) LG_PRE(9, true, 6, false); else if (small) LG_PRE(9, false, 1, true); else LG_PRE(9, false, 4, true);
+    if (ticket) LG_PRE(9, true, 6, false); else if (small) LG_PRE(9, false, 3, true); else LG_PRE(9, false, 4, true);
   } else {
-    if (ticket) LG_PRE(18, true, 6, false); else if (small) LG_PRE(18, false, 1, true); else LG_PRE(18, false, 4, true);
+    if (ticket) LG_PRE(18, true, 6, false); else if (small) LG_PRE(18, false, 3, true); else LG_PRE(18, false, 4, true);
   }
 #undef LG_PRE
   return check_launch("pre_physics_kernel");

@@ -141,7 +141,7 @@ __device__ __noinline__ void action_noise(const LgParams& P, uint64_t genv, uint
 // They meet for the resets (block-uniform branch: eight reset sub-tasks over the eight warps, lane = listed env);
 // the row group then computes the torque from the shared-memory slabs while the scan group resolves its look-back;
 // action and torque rows leave as bulk stores.
-// MINB = CTAs per SM the register allocation must allow: 1 (80 registers, 3 CTAs per SM) for grids of one wave, where
+// MINB = CTAs per SM the register allocation must allow: 3 (<= 85 registers) for grids of one wave, where
 // the kernel is a latency chain (30 % resets at 16 384 envs: 17.3 against 18.0 us/step), 4 (64 registers) for larger
 // grids, where more rows in flight per SM is what counts (65 536 envs with goal resampling: 37.7 against 42.3 us/step).
 //
@@ -333,24 +333,31 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
         reset_subtask(P, S, B, env, sub, dr, (ent & 0x8000) != 0, s_dof + local * 18);
       }
     };
-    // the two long sub-tasks (object pose: 2 Philox blocks, sqrt, 2 sincos; goal: 2-3 blocks, Box-Muller, normalise)
-    // take two and three warps, the six short ones (joint blocks 0..4, bookkeeping) two each of the other three
-    if (SPLIT) {
-      if (warp < 2) run_sub(5, warp * 32 + lane, 64);
-      else if (warp < 5) run_sub(6, (warp - 2) * 32 + lane, 96);
-      else { run_sub(warp - 5, lane, 32); run_sub(warp == 7 ? 7 : warp - 2, lane, 32); }
-    } else {   // four warps: the long sub-tasks on two warps each, then the six short ones
-      run_sub(warp < 2 ? 5 : 6, tid & 63, 64);
-      run_sub(warp, lane, 32);                                   // joint blocks 0..3
-      if (warp < 2) run_sub(warp == 0 ? 4 : 7, lane, 32);        // joint block 4, bookkeeping
-    }
+    // Work items = (sub-task, chunk of 32 listed envs).  The four long sub-tasks (object position 5 / yaw 8, goal
+    // position 6 / orientation 9) come first, one item per warp; the six short ones (joint blocks 0..4, bookkeeping 7)
+    // follow, dealt round-robin.
+    constexpr int kWarps = NT / 32;
+    {
+      const int long_subs[4] = {5, 8, 6, 9};
+      if (SPLIT) run_sub(long_subs[warp >> 1], (warp & 1) * 32 + lane, 64);   // two warps per long sub-task
+      else run_sub(long_subs[warp], lane, 32);
+      const int short_subs[6] = {0, 1, 2, 3, 4, 7};
+      constexpr int kChunks = SPLIT ? 2 : 1;
 #pragma unroll 1
-    for (int r = tid; r < nb; r += NT) {   // goal resets second, as in env_base.py:374-379
-      const int64_t env = e0 + s_goal_list[r];
-      const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
-                                       (int64_t)ex_b + r);
-      B.goal_reset[env] = 0;  // trifinger_env.py:427
-      apply_goal_sample(P, S, B, env, dr);
+      for (int item = warp; item < 6 * kChunks; item += kWarps)
+        run_sub(short_subs[item / kChunks], (item % kChunks) * 32 + lane, 32 * kChunks);
+    }
+    // goal resets second, as in env_base.py:374-379: position and orientation halves on different halves of the CTA
+    if (nb) {
+      const int half = tid >= NT / 2 ? 1 : 0, t2 = tid - half * (NT / 2);
+#pragma unroll 1
+      for (int r = t2; r < nb; r += NT / 2) {
+        const int64_t env = e0 + s_goal_list[r];
+        const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
+                                         (int64_t)ex_b + r);
+        if (half == 0) B.goal_reset[env] = 0;  // trifinger_env.py:427
+        apply_goal_sample(P, S, B, env, dr, half);
+      }
     }
     LG_TP(1, 7, tid == 0);
     __syncthreads();   // the mirrored joint rows are final before the torque reads them
