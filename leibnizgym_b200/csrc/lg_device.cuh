@@ -290,7 +290,7 @@ __device__ __forceinline__ void sample_goal_position(const LgParams& P, const fl
   }
   pos[0] = x; pos[1] = y; pos[2] = z;
 }
-__device__ __forceinline__ void sample_goal_orientation(const LgParams& P, const DrawSource& dr, float yaw_u, float quat[4],
+__device__ __forceinline__ void sample_goal_orientation(const LgParams& P, const DrawSource dr, float yaw_u, float quat[4],
                                                         float angvel[3]) {
   const int d = P.task_difficulty;
   Quat q{0.0f, 0.0f, 0.0f, 1.0f};
@@ -316,7 +316,7 @@ __device__ __forceinline__ void sample_goal_orientation(const LgParams& P, const
 // Write the sampled goal into the goal buffers and the goal actor's root row (trifinger_env.py:1248-1265):
 // `half` 0 = position (+ the row's linear velocity), 1 = orientation and angular velocity, 2 = both.
 __device__ __noinline__ void apply_goal_sample(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                               int64_t e, const DrawSource& dr, int half = 2) {
+                                               int64_t e, const DrawSource dr, int half = 2) {
   float* gp = B.goal_pose + e * 7;
   float* gm = B.goal_movement + e * 6;
   float* row = S.root_state + ((int64_t)P.actors_per_env * e + P.goal_slot) * 13;
@@ -357,7 +357,7 @@ constexpr int kResetSubtasks = 10;
 // Out of line on purpose: the fused kernel reaches it from several call sites behind a block-uniform branch that most
 // tiles never take; one copy keeps the kernel's hot path (no resets) small enough to sit in the instruction cache.
 __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
-                                           int sub, const DrawSource& dr, bool goal_reset_follows,
+                                           int sub, const DrawSource dr, bool goal_reset_follows,
                                            float* dof_mirror = nullptr) {
   if (sub < 5) {
     if (P.robot_reset == LG_RESET_NONE) return;
@@ -422,7 +422,7 @@ __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& 
 
 // all of it for one env, in the reference's order (hooks on explicit id lists)
 __device__ __forceinline__ void reset_one_env(const LgParams& P, const LgSimState& S, const LgBuffers& B,
-                                              int64_t e, const DrawSource& dr) {
+                                              int64_t e, const DrawSource dr) {
   reset_subtask(P, S, B, e, 7, dr, false);
   for (int sub = 0; sub < kResetSubtasks; ++sub)
     if (sub != 7) reset_subtask(P, S, B, e, sub, dr, false);
