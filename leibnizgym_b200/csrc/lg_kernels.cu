@@ -309,8 +309,9 @@ cudaError_t err;
     return (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
   }();
   const bool small = tiles <= resident_small;
+  const lg::PreHot hot = {action_in, S->dof_state, B->applied_torque, P->num_envs, tiles, 0};
 #define LG_PRE(AD, TK, MB, SP) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB, SP>, (unsigned)tiles, \
-                                              SP ? lg::kPreThreads : lg::kScanThreads, st, *P, *S, *B, action_in, tiles)
+                                              SP ? lg::kPreThreads : lg::kScanThreads, st, hot, *P, *S, *B)
   if (P->action_dim == 9) {
     if (ticket) LG_PRE(9, true, 6, false); else if (small) LG_PRE(9, false, 3, true); else LG_PRE(9, false, 4, true);
   } else {

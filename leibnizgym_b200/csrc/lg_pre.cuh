@@ -132,6 +132,19 @@ __device__ __noinline__ void action_noise(const LgParams& P, uint64_t genv, uint
   }
 }
 
+// What the first instructions of the kernel need, as the FIRST kernel parameter: kernel parameters sit in the constant
+// bank in a buffer of their own per launch, so every 64-byte line of them costs a constant-cache miss on first use;
+// the slab copies can be issued after one miss instead of four (pointers otherwise spread over LgSimState, LgBuffers,
+// LgParams and the trailing arguments).
+struct PreHot {
+  const float* action_in;
+  const float* dof_state;
+  float* applied_torque;
+  int64_t num_envs;
+  int32_t num_tiles;
+  int32_t _pad;
+};
+
 // One CTA = one tile of 128 envs, two 128-thread groups working on two independent chains:
 //   row group  (warps 0-3, thread = env): the tile's action and joint-state rows arrive as TMA bulk copies; the action
 //              row is clamped (+ noise, extension), zeroed for resetting envs and kept for the torque;
@@ -151,9 +164,10 @@ __device__ __noinline__ void action_noise(const LgParams& P, uint64_t genv, uint
 // 54 us).  Used together with the ticket path.
 template <int A, bool TICKET, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kPreThreads : kScanThreads, MINB)
-pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ LgSimState S,
-                   const __grid_constant__ LgBuffers B,
-                   const float* __restrict__ action_in, int num_tiles) {
+pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgParams P,
+                   const __grid_constant__ LgSimState S, const __grid_constant__ LgBuffers B) {
+  const float* __restrict__ action_in = H.action_in;
+  const int num_tiles = H.num_tiles;
   constexpr int E = kPreTile;
   __shared__ __align__(128) float s_act[E * A];
   __shared__ __align__(128) float s_dof[E * 18];
@@ -184,9 +198,9 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
   }
   const int64_t e0 = (int64_t)tile * E;
   const int64_t e = e0 + gt;               // this thread's env (both groups)
-  const int nvalid = (int)min((int64_t)E, P.num_envs - e0);
+  const int nvalid = (int)min((int64_t)E, H.num_envs - e0);
   const bool live = gt < nvalid;
-  const bool want_torque = B.applied_torque != nullptr;
+  const bool want_torque = H.applied_torque != nullptr;
   const bool full_tile = nvalid == E;   // bulk copies need 16-byte multiples: ragged last tile goes lane by lane
 
   // ---- row group: every global load of the tile's rows up front ------------------------------------------
@@ -196,7 +210,7 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
         mbar_init(&s_mbar, 1);
         mbar_expect_tx(&s_mbar, (uint32_t)(sizeof(float) * E * (A + (want_torque ? 18 : 0))));
         bulk_load(s_act, action_in + e0 * A, sizeof(float) * E * A, &s_mbar);
-        if (want_torque) bulk_load(s_dof, S.dof_state + e0 * 18, sizeof(float) * E * 18, &s_mbar);
+        if (want_torque) bulk_load(s_dof, H.dof_state + e0 * 18, sizeof(float) * E * 18, &s_mbar);
       }
     } else if (live) {
 #pragma unroll
@@ -224,15 +238,6 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
       if (B.force_reset) flag_r |= B.force_reset[e];             // `_reset_buf |= mask` folded into the pass
       if (B.force_goal_reset) flag_g |= B.force_goal_reset[e];
     }
-    if (tile == 0 && gt < LG_NUM_STATS && B.step_stats) B.step_stats[gt] = 0.0;  // accumulated by lg_post_physics
-    if (tile == 0 && gt == kScanThreads - 1 && P.use_device_clock) {
-      // device clock: advance the frame counter and publish the reward coefficients of the coming
-      // post-physics pass (env_steps_count = frames x global env count, envs/env_base.py:286-289);
-      // done by an otherwise idle lane while the flag bytes are in flight
-      const int64_t frame = B.control->frame_count + P.control_decimation;
-      B.control->frame_count = frame;
-      if (B.reward_coef) compute_coefs(P, (double)(frame * P.global_num_envs), B.reward_coef);
-    }
     f_reset = flag_r != 0; f_goal = flag_g != 0;
     tile_scan_local<1>(f_reset, f_goal, gt, s_wa, s_wb, t);
     s_flag[gt] = (uint8_t)((f_reset ? 1 : 0) | (f_goal ? 2 : 0));
@@ -245,6 +250,16 @@ pre_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ L
       s_scan[0] = t.total_a; s_scan[1] = t.total_b;
     }
     LG_TP(1, 3, tid == NT - kScanThreads);
+    // Tile 0's housekeeping comes AFTER its aggregate is published: every other tile's look-back ends at tile 0's
+    // inclusive prefix, and the coefficient arithmetic below is a chain of fp64 operations.
+    if (tile == 0 && gt < LG_NUM_STATS && B.step_stats) B.step_stats[gt] = 0.0;  // accumulated by lg_post_physics
+    if (tile == 0 && gt == kScanThreads - 1 && P.use_device_clock) {
+      // device clock: advance the frame counter and publish the reward coefficients of the coming
+      // post-physics pass (env_steps_count = frames x global env count, envs/env_base.py:286-289)
+      const int64_t frame = B.control->frame_count + P.control_decimation;
+      B.control->frame_count = frame;
+      if (B.reward_coef) compute_coefs(P, (double)(frame * P.global_num_envs), B.reward_coef);
+    }
   }
   __syncthreads();   // flags, tile totals and reset lists are visible to everyone; the mbarrier is initialised
   const int na = (int)s_scan[0], nb = (int)s_scan[1];

@@ -89,8 +89,13 @@ def main():
     print(f"{N} envs, workload {a.workload}, post_only={a.post_only}: {us:.2f} us per step (CUDA events)")
     post_ctas = min(8192, (N + 27) // 28 if N <= 16576 else (N + 31) // 32)
     pre_ctas = min(8192, (N + 127) // 128)
-    tp, _ = read_trace(lib, 0, post_ctas)
-    tp = tp[tp[:, 0] > 0]
+    tp, cp = read_trace(lib, 0, post_ctas)
+    ok = tp[:, 0] > 0
+    tp, cp = tp[ok], cp[ok]
+    # SM clock actually seen inside the kernel: cycles between two stamps of a CTA over the nanoseconds between them
+    dt, dc = (tp[:, 9] - tp[:, 1]).astype(np.float64), (cp[:, 9] - cp[:, 1]).astype(np.float64)
+    good = dt > 500
+    print(f"SM clock inside the post kernel (dependency wait -> last store, per CTA): median {np.median(dc[good] / dt[good]) * 1e3:.0f} MHz")
     for k in [k for k in POST if (tp[:, k] == 0).all()]:
         POST.pop(k)    # points the traced kernel variant does not stamp
     if not a.post_only:
