@@ -156,7 +156,8 @@ typedef struct LgControl {
   uint32_t scan_ticket;   /* tile ticket dispenser of the ordered compaction                        */
   uint32_t scan_epoch;    /* validity tag of the look-back status words; advances once per compaction
                              launch and doubles as the RNG epoch of the fused resets                */
-  uint32_t _pad[2];
+  uint32_t scan_readers;  /* direct-prefix variant of lg_pre_physics: tiles that have read their predecessors' flags */
+  uint32_t scan_exits;    /* ... and tiles that have finished; the last one re-arms both and advances scan_epoch   */
 } LgControl;
 
 /* The simulator-owned tensors (zero-copy views in the reference, trifinger_env.py:602-617). */

@@ -70,7 +70,7 @@ class LgParams(C.Structure):
 
 class LgControl(C.Structure):
     _fields_ = [("rng_epoch", C.c_uint64), ("frame_count", C.c_int64), ("scan_ticket", C.c_uint32),
-                ("scan_epoch", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+                ("scan_epoch", C.c_uint32), ("scan_readers", C.c_uint32), ("scan_exits", C.c_uint32)]
 
 
 class LgSimState(C.Structure):

@@ -358,7 +358,7 @@ constexpr int kResetSubtasks = 10;
 // tiles never take; one copy keeps the kernel's hot path (no resets) small enough to sit in the instruction cache.
 __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& S, const LgBuffers& B, int64_t e,
                                            int sub, const DrawSource dr, bool goal_reset_follows,
-                                           float* dof_mirror = nullptr) {
+                                           float* dof_mirror = nullptr, bool clear_flag = true) {
   if (sub < 5) {
     if (P.robot_reset == LG_RESET_NONE) return;
     float* dof = S.dof_state + e * 18;
@@ -412,7 +412,7 @@ __device__ __noinline__ void reset_subtask(const LgParams& P, const LgSimState& 
     // 6: goal position, 9: goal orientation + angular velocity
     if (!goal_reset_follows) apply_goal_sample(P, S, B, e, dr, sub == 6 ? 0 : 1);
   } else {
-    B.reset[e] = 0;
+    if (clear_flag) B.reset[e] = 0;   // (the fused kernel's direct-prefix variant clears its tile's flags itself, later)
     B.steps_count[e] = 0;
     B.successes[e] = 0;
     float* act = B.action + e * P.action_dim;

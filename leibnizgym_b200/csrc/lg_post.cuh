@@ -282,6 +282,8 @@ __device__ __noinline__ double stat_sums_fp64(float t0, float t1, float t2, floa
   return mine;
 }
 
+constexpr int kCombineWarp = 3;   // the reward warp with the shortest sub-task (previous angle) also combines
+
 // ======== reward warps: lane = env, warp = sub-task (uniform control flow inside a warp) ================
 // Called by the four reward warps (threads 0..127) of a post-physics CTA once the tile's object pose, goal pose,
 // fingertip positions and previous history entry are staged in shared memory (raw, unscaled); E <= 32 envs per tile.
@@ -379,19 +381,20 @@ __device__ __forceinline__ void reward_subtasks(const LgParams& P, int nvalid,
   }
 }
 
-// Second half of the reward chain, called by the four reward warps after they have put their own columns into the
-// output tile: they meet, then warp 0 combines the sub-task results, terminates, counts and accumulates the statistics.
+// Second half of the reward chain, called by the combine warp (kCombineWarp) alone, after it has stored its own
+// columns: it waits for the other three reward warps' arrival at barrier 1, then combines the sub-task results,
+// terminates, counts and accumulates the statistics.
 template <int E, bool EXT>
 __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffers& B, int64_t e0, int nvalid,
                                                const float* s_coef, const float* s_part,
                                                uint8_t in_goal_reset, uint8_t in_succ, uint8_t in_reset, int64_t in_steps,
                                                const StatScale& stat_scale) {
   const int tid = threadIdx.x;
-  const int rw = tid >> 5, renv = tid & 31;
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four reward warps
-  LG_TP(0, 6, tid == 0);
-  if (rw == 0) {
-    // ---- warp 0: combine, terminate, count (one lane per env) -----------------------------------------
+  const int renv = tid & 31;
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the other three reward warps have arrived: their results are in s_part
+  LG_TP(0, 6, renv == 0);
+  {
+    // ---- combine, terminate, count (one lane per env) -------------------------------------------------
     const int env = renv;
     const bool live = renv < nvalid;
     float terms[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // per-env values of the statistics (0 beyond the tile)
@@ -442,7 +445,7 @@ __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffer
       dn = reset && goal_reset;
       if (B.dones) B.dones[e] = dn;
     }
-    LG_TP(0, 7, tid == 0);
+    LG_TP(0, 7, renv == 0);
     // ---- episode statistics (trifinger_env.py:554, :1067-1068, :1076, :1098-1099): per-CTA sums over the warp's
     // lanes (lane = env), lane s keeps slot s, then ONE reduction instruction carries all slots of the CTA to the 104
     // contiguous bytes of the statistics vector — no fence, no second kernel, one L2 atomic transaction per CTA (one
@@ -459,7 +462,7 @@ __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffer
     const unsigned m_succ = __ballot_sync(0xffffffffu, succ), m_reset = __ballot_sync(0xffffffffu, reset);
     const unsigned m_dn = __ballot_sync(0xffffffffu, dn);
     double mine;
-    LG_TP(0, 23, tid == 0);
+    LG_TP(0, 23, renv == 0);
     if (__all_sync(0xffffffffu, fits)) {
       // all eight sums unconditionally (an inactive term contributes zeros): no branches between them, so the
       // conversions and reductions of the slots overlap
@@ -469,7 +472,7 @@ __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffer
         const float x = k < 7 ? (((active >> k) & 1) ? terms[k] : 0.0f) : reward;
         tot[k] = warp_sum_i64(__float2ll_rn(x * kStatFixScale));   // scaling by 2^30 is exact
       }
-      LG_TP(0, 24, tid == 0);
+      LG_TP(0, 24, renv == 0);
       long long fixed = 0;
 #pragma unroll
       for (int k = 0; k < 7; ++k)
@@ -496,9 +499,9 @@ __device__ __forceinline__ void reward_combine(const LgParams& P, const LgBuffer
 #ifdef LG_TRACE
     if (mine == 1.2345e300) return;   // make the stamp below wait for the scaled value
 #endif
-    LG_TP(0, 25, tid == 0);
+    LG_TP(0, 25, renv == 0);
     if (env <= LG_STAT_DONES) atomicAdd(B.step_stats + env, mine);
-    LG_TP(0, 8, tid == 0);
+    LG_TP(0, 8, renv == 0);
   }
 }
 
@@ -529,7 +532,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   if (role >= R::R_END) role -= (R::LANES - R::R_END);  // spare lanes duplicate a column (same value, same address)
   const bool front = (tid % R::LANES) / 32 * 32 < R::FRONT;  // warp-uniform: this warp holds obs/stage/history roles
   StatScale stat_scale = {0.0, 0, false};
-  if (REWARD && tid < 32) stat_scale = stat_lane_scale(P, tid);   // statistics lanes: warp 0 (prologue work)
+  if (REWARD && (tid >> 5) == kCombineWarp) stat_scale = stat_lane_scale(P, tid & 31);   // statistics lanes (prologue work)
   const int env_first = (tid / R::LANES) * EP;     // first env (within the tile) of this lane's part
   const float* src;             // source of (env_first, column)
   int stride;                   // source row stride in floats
@@ -582,7 +585,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   int64_t in_steps = 0;
   if (rlive) {
     hprev = ld_hist4(hist_src);
-    if (rw == 0) { in_goal_reset = *p_goal_reset; in_succ = *p_succ; in_reset = *p_reset; in_steps = *p_steps; }
+    if (rw == kCombineWarp) { in_goal_reset = *p_goal_reset; in_succ = *p_succ; in_reset = *p_reset; in_steps = *p_steps; }
   }
   float v[EP];
   if (full) {
@@ -731,13 +734,20 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
         if (FULLC || k < cnt) g_dst[k * 7] = g_src[(int64_t)k * actor_stride];
     }
   };
+  // Order of the tail, per warp: the three reward warps with the longer sub-tasks only ARRIVE at the reward barrier
+  // and go on to their columns; the warp with the shortest sub-task (kCombineWarp) stores its columns first — by
+  // then the others have arrived — and then combines, terminates and accumulates the statistics.  No warp waits,
+  // and the CTA's longest chain is sub-task -> combine -> statistics instead of that plus a column pass.
   if (REWARD && rw < 4) {
     reward_subtasks<E, EXT>(P, nvalid, s_obj, s_goal, s_tips, s_hist, s_coef, &s_part[0][0]);
-    reward_combine<E, EXT>(P, B, e0, nvalid, s_coef, &s_part[0][0], in_goal_reset, in_succ, in_reset, in_steps, stat_scale);
+    if (rw != kCombineWarp) asm volatile("bar.arrive 1, 128;" ::: "memory");
   }
   if (full) emit_outputs(std::true_type{});
   else emit_outputs(std::false_type{});
-  LG_TP(0, 9, tid == 0); LG_TP(0, 15, tid == 128); LG_TP(0, 19, tid == 32); LG_TP(0, 20, tid == 64); LG_TP(0, 21, tid == 96);
+  LG_TP(0, 9, tid == 0);
+  if (REWARD && rw == kCombineWarp)
+    reward_combine<E, EXT>(P, B, e0, nvalid, s_coef, &s_part[0][0], in_goal_reset, in_succ, in_reset, in_steps, stat_scale);
+  LG_TP(0, 15, tid == 128); LG_TP(0, 19, tid == 32); LG_TP(0, 20, tid == 64); LG_TP(0, 21, tid == 96);
 }
 
 // history seeding (trifinger_env.py:619-628): both entries = initial simulator state

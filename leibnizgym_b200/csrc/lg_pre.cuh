@@ -115,6 +115,72 @@ __device__ __forceinline__ void tile_scan_local(bool fa, bool fb, int gt, uint32
   t.total_a = ta; t.total_b = tb;
 }
 
+// ---- direct prefix (grids of at most kDirectMaxTiles tiles) ------------------------------------------------------
+// Instead of waiting for its predecessors' aggregates, a CTA counts the flagged envs in front of its tile ITSELF: the
+// flag bytes of all predecessors (at most 127 x 128 bytes per mask, hot in L2) are fetched as 128-bit words by all 256
+// threads right at entry — addresses known at launch, one round trip — and counted next to the tile's own block scan.
+// No CTA ever waits for another one's progress, so a late tile cannot hold up the rest of the grid (look-back done:
+// median 2.0, max 3.0 us after entry).
+constexpr int kDirectMaxTiles = 128;
+constexpr int kDirectVecs = (kDirectMaxTiles - 1) * kPreTile / 16 / kPreThreads + 1;   // 128-bit words per thread and mask: 4
+
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {   // how many of the four bytes are != 0
+  return (uint32_t)__popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);
+}
+// count | count << 16 of the flagged envs among the first `nvec` x 16 envs, the share of thread `tid` of the CTA.
+// The forced masks (`_reset_buf |= mask`) are optional.  Flag bytes are 0 or 1 wherever they come from a bool tensor:
+// one dot-product instruction per word sums them; any other non-zero value (seen in the OR of all words) sends the
+// thread through the exact count.
+__device__ __forceinline__ uint32_t count_flagged_before(const uint8_t* __restrict__ reset, const uint8_t* __restrict__ goal,
+                                                         const uint8_t* __restrict__ force_reset,
+                                                         const uint8_t* __restrict__ force_goal, int nvec, int tid) {
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  uint4 vr[kDirectVecs], vg[kDirectVecs];
+#pragma unroll
+  for (int k = 0; k < kDirectVecs; ++k) {
+    const int i = tid + k * kPreThreads;
+    vr[k] = i < nvec ? __ldcg(reinterpret_cast<const uint4*>(reset) + i) : zero;
+    vg[k] = i < nvec ? __ldcg(reinterpret_cast<const uint4*>(goal) + i) : zero;
+  }
+  if (force_reset) {
+#pragma unroll
+    for (int k = 0; k < kDirectVecs; ++k) {
+      const int i = tid + k * kPreThreads;
+      if (i < nvec) {
+        const uint4 f = __ldcg(reinterpret_cast<const uint4*>(force_reset) + i);
+        vr[k].x |= f.x; vr[k].y |= f.y; vr[k].z |= f.z; vr[k].w |= f.w;
+      }
+    }
+  }
+  if (force_goal) {
+#pragma unroll
+    for (int k = 0; k < kDirectVecs; ++k) {
+      const int i = tid + k * kPreThreads;
+      if (i < nvec) {
+        const uint4 f = __ldcg(reinterpret_cast<const uint4*>(force_goal) + i);
+        vg[k].x |= f.x; vg[k].y |= f.y; vg[k].z |= f.z; vg[k].w |= f.w;
+      }
+    }
+  }
+  uint32_t a = 0, b = 0, any = 0;
+#pragma unroll
+  for (int k = 0; k < kDirectVecs; ++k) {
+    const uint4 x = vr[k], y = vg[k];
+    a = __dp4a(x.x, 0x01010101u, a); a = __dp4a(x.y, 0x01010101u, a); a = __dp4a(x.z, 0x01010101u, a); a = __dp4a(x.w, 0x01010101u, a);
+    b = __dp4a(y.x, 0x01010101u, b); b = __dp4a(y.y, 0x01010101u, b); b = __dp4a(y.z, 0x01010101u, b); b = __dp4a(y.w, 0x01010101u, b);
+    any |= (x.x | x.y) | (x.z | x.w) | (y.x | y.y) | (y.z | y.w);
+  }
+  if (any & 0xfefefefeu) {   // cold: a flag byte other than 0 / 1
+    a = 0; b = 0;
+#pragma unroll
+    for (int k = 0; k < kDirectVecs; ++k) {
+      a += nonzero_bytes(vr[k].x) + nonzero_bytes(vr[k].y) + nonzero_bytes(vr[k].z) + nonzero_bytes(vr[k].w);
+      b += nonzero_bytes(vg[k].x) + nonzero_bytes(vg[k].y) + nonzero_bytes(vg[k].z) + nonzero_bytes(vg[k].w);
+    }
+  }
+  return a | (b << 16);
+}
+
 // extension (no reference code): additive Gaussian noise on one env's action row — one Philox block -> four normals ->
 // four action columns.  Out of line: off by default, and the hot path should not carry its code.
 template <int A>
@@ -162,7 +228,7 @@ struct PreHot {
 // every predecessor has long published): grids of many waves are bound by the rows in flight per SM, not by the length
 // of a CTA's chain, and half-idle CTAs of 256 threads cost them a third of their throughput (1 048 576 envs: 84 against
 // 54 us).  Used together with the ticket path.
-template <int A, bool TICKET, int MINB, bool SPLIT>
+template <int A, bool TICKET, int MINB, bool SPLIT, bool DIRECT = false>
 __global__ void __launch_bounds__(SPLIT ? kPreThreads : kScanThreads, MINB)
 pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgParams P,
                    const __grid_constant__ LgSimState S, const __grid_constant__ LgBuffers B) {
@@ -178,6 +244,9 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
   __shared__ uint8_t s_flag[E];            // bit 0 reset, bit 1 goal reset
   __shared__ uint32_t s_scan[4];           // tile totals (a, b) and the global exclusive prefix (a, b)
   __shared__ uint16_t s_reset_list[E], s_goal_list[E];
+  __shared__ uint32_t s_before[kPreThreads / 32];   // DIRECT: flagged envs in front of the tile, per warp
+
+  static_assert(!DIRECT || (SPLIT && !TICKET), "the direct prefix is a variant of the two-group, co-resident kernel");
   const int tid = threadIdx.x;
   constexpr int NT = SPLIT ? kPreThreads : kScanThreads;   // threads of the CTA
   const int gt = tid & (kScanThreads - 1);
@@ -224,6 +293,8 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
   LG_TP(1, 1, tid == 0);
   pdl_wait();   // the flags, counters and statistics below are results of the preceding post-physics pass
   LG_TP(1, 2, tid == 0);
+  uint32_t before = 0;   // DIRECT: this thread's share of the flagged envs in front of the tile (a | b << 16)
+  if (DIRECT) before = count_flagged_before(B.reset, B.goal_reset, B.force_reset, B.force_goal_reset, tile * (E / 16), tid);
 
   // ---- scan group: block scan of both masks + aggregate publication (env_base.py:374-379) ------------------
   // Needs only the two flag bytes, so the tile's aggregate is visible to its successors while the action /
@@ -244,9 +315,11 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
     if (f_reset) s_reset_list[t.rank_a] = (uint16_t)(gt | (f_goal ? 0x8000 : 0));   // flagged envs by rank in the tile
     if (f_goal) s_goal_list[t.rank_b] = (uint16_t)gt;
     if (gt == 0) {
-      const uint64_t st = tile == 0 ? kStateInclusive : kStateAggregate;
-      atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
-                 (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
+      if (!DIRECT) {
+        const uint64_t st = tile == 0 ? kStateInclusive : kStateAggregate;
+        atomicExch(reinterpret_cast<unsigned long long*>(B.scan_status + tile),
+                   (unsigned long long)pack_status(epoch, st, t.total_a, t.total_b));
+      }
       s_scan[0] = t.total_a; s_scan[1] = t.total_b;
     }
     LG_TP(1, 3, tid == NT - kScanThreads);
@@ -261,17 +334,51 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
       if (B.reward_coef) compute_coefs(P, (double)(frame * P.global_num_envs), B.reward_coef);
     }
   }
+  if (DIRECT) {
+    before = __reduce_add_sync(0xffffffffu, before);
+    if ((tid & 31) == 0) s_before[tid >> 5] = before;
+  }
   __syncthreads();   // flags, tile totals and reset lists are visible to everyone; the mbarrier is initialised
   const int na = (int)s_scan[0], nb = (int)s_scan[1];
   const bool resets = (na | nb) != 0;                         // block-uniform
   const bool rank_first = resets && P.inject_draws != 0;      // injected draws are indexed by compaction rank
+  // DIRECT: grid-wide hand-shake about the flag bytes, kept off the row group's chain (one thread of the scan group,
+  // which has slack).  `scan_readers` counts the tiles whose reads of their predecessors' flag bytes have completed (the
+  // values went into the counts); a tile that is going to CLEAR flag bytes (resets) first waits for all of them.
+  // `scan_exits` counts the tiles that no longer look at `scan_readers`; the last one re-arms both and advances the
+  // epoch (the RNG epoch of the fused resets), which every thread of the grid has read at entry by then.
+  auto tile_passed = [&]() {
+    if (atomicAdd(&B.control->scan_exits, 1u) == (uint32_t)num_tiles - 1u) {
+      B.control->scan_readers = 0; B.control->scan_exits = 0;
+      B.control->scan_epoch = epoch + 1;
+    }
+  };
+  const bool handshake = DIRECT && tid == NT - 2;   // a thread of the scan group without other duties
+  uint32_t direct_a = 0, direct_b = 0;   // DIRECT: the global exclusive prefix, known to every thread from here on
+  if (DIRECT) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < kPreThreads / 32; ++w) sum += s_before[w];
+    direct_a = sum & 0xffffu; direct_b = sum >> 16;
+    if (handshake) {
+      __threadfence();
+      atomicAdd(&B.control->scan_readers, 1u);
+      if (!resets) tile_passed();
+    }
+  }
 
   // ---- scan group: global exclusive prefix, then the ordered id lists (env_base.py:374-379;
   // trifinger_env.py:413-416, :435-436).  Runs next to the row group's work; a tile with resets does it after them
   // (every warp helps with the resets) unless the injected test draws need the rank first.
   auto finish_scan = [&]() {
-    uint32_t ex_a = 0, ex_b = 0;
-    tile_scan_finish<TICKET, 1>(B.control, B.scan_status, t, num_tiles, gt, ex_a, ex_b, B.counts);
+    uint32_t ex_a = direct_a, ex_b = direct_b;
+    if (DIRECT) {
+      if (gt == 0 && tile == num_tiles - 1 && B.counts) {
+        B.counts[0] = (int32_t)(ex_a + t.total_a); B.counts[1] = (int32_t)(ex_b + t.total_b);
+      }
+    } else {
+      tile_scan_finish<TICKET, 1>(B.control, B.scan_status, t, num_tiles, gt, ex_a, ex_b, B.counts);
+    }
     if (gt == 0) { s_scan[2] = ex_a; s_scan[3] = ex_b; }
     if (f_reset) {
       const int64_t j = (int64_t)ex_a + t.rank_a;
@@ -345,7 +452,7 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
         const int64_t env = e0 + local;
         const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeReset, B.inject_reset_u, B.inject_reset_n,
                                          (int64_t)ex_a + r);
-        reset_subtask(P, S, B, env, sub, dr, (ent & 0x8000) != 0, s_dof + local * 18);
+        reset_subtask(P, S, B, env, sub, dr, (ent & 0x8000) != 0, s_dof + local * 18, !DIRECT);
       }
     };
     // Work items = (sub-task, chunk of 32 listed envs).  The four long sub-tasks (object position 5 / yaw 8, goal
@@ -370,12 +477,23 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
         const int64_t env = e0 + s_goal_list[r];
         const DrawSource dr = make_draws(P, (uint64_t)epoch, env, kPurposeGoal, B.inject_goal_u, B.inject_goal_n,
                                          (int64_t)ex_b + r);
-        if (half == 0) B.goal_reset[env] = 0;  // trifinger_env.py:427
+        if (!DIRECT && half == 0) B.goal_reset[env] = 0;  // trifinger_env.py:427
         apply_goal_sample(P, S, B, env, dr, half);
       }
     }
     LG_TP(1, 7, tid == 0);
+    if (handshake) {
+      // the flag bytes of this tile may only be cleared once no tile reads them any more (all tiles run: the grid is
+      // co-resident; by now — a whole reset phase after the reads were issued — the wait is over before it starts)
+      while (ld_volatile_u32(&B.control->scan_readers) < (uint32_t)num_tiles) {}
+      __threadfence();
+    }
     __syncthreads();   // the mirrored joint rows are final before the torque reads them
+    if (handshake) tile_passed();
+    if (DIRECT) {      // trifinger_env.py:382 (`_reset_buf[env_ids] = 0`), :427
+      for (int r = tid; r < na; r += NT) B.reset[e0 + (s_reset_list[r] & 0x7fff)] = 0;
+      for (int r = tid; r < nb; r += NT) B.goal_reset[e0 + s_goal_list[r]] = 0;
+    }
     if (SPLIT && !rank_first && scan_group) finish_scan();
   }
   // ---- moving goal (__update_goal_movement_pre, trifinger_env.py:1267-1277): every step the goal body's
@@ -395,7 +513,10 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
   pdl_launch_dependents();
   if (full_tile) {
     fence_async_proxy();           // generic-proxy writes to the slabs -> visible to the bulk-copy engine
-    __syncthreads();
+    // the slabs that leave are written by the row group alone: the scan group (still busy with its id lists, or waiting
+    // for an atomic's answer) is not waited for
+    if (!SPLIT) __syncthreads();
+    else if (row_group) group_sync<2>();
     if (tid == 0) {
       bulk_store(B.action + e0 * A, s_act, sizeof(float) * E * A);
       if (want_torque) bulk_store(B.applied_torque + e0 * 9, s_tq, sizeof(float) * E * 9);

@@ -54,7 +54,7 @@ def launch_list():
         a[0] += 1
         a[1] += float(r[iV].replace(",", ""))
     total = sum(a[1] for a in agg.values())
-    out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 128 --warmup 32 --no-cpu --e2e-steps 8",
+    out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 64 --warmup 16 --no-cpu --no-e2e --min-timed-ms 2",
            "(first 600 launches of the process: env construction, graph captures, warm-up, timed region; cold-cache, serialised)", ""]
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{k:<72s} n={n:4d} avg_ns={ns / n:9.0f} share={100 * ns / total:5.1f}%")

@@ -239,3 +239,58 @@ def test_observed_parity_errors_are_recorded():
         assert w["max_abs_beyond_rtol"] <= ATOL[key], (key, w, ATOL[key])
         # the floor is not slack for its own sake: at most 4x what is observed (or the 1e-6 resolution of the check)
         assert ATOL[key] <= max(4.0 * w["max_abs_beyond_rtol"], 1e-6), (key, w, ATOL[key])
+
+
+# ---- direct prefix of the pre-physics pass (32..128 tiles): counts the flagged envs in front of each tile itself -------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [16_384, 12_336])   # 128 full tiles | 96 tiles + a ragged one (masks stay 16-byte aligned)
+def test_direct_prefix_equals_lookback_bit_for_bit(N):
+    """The same scenario (30 % forced resets, 5 % goal resets, graph replay + eager steps; scripts/digest_step.py) through
+    the direct-prefix instantiation and, in a second process, through the look-back one (LG_PRE_DIRECT=0): every buffer,
+    every id list and the statistics must be identical."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, LG_PRE_DIRECT=mode)
+        res = subprocess.run([sys.executable, os.path.join(root, "scripts", "digest_step.py"), str(N)], env=env,
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[mode] = res.stdout
+    assert "graph" in out["1"] and "eager" in out["1"]
+    assert out["1"] == out["0"]
+
+
+@pytest.mark.gpu
+def test_direct_prefix_counts_any_nonzero_flag_byte():
+    """The compaction treats a flag byte as set when it is != 0 (the look-back path tests `!= 0` per env); the direct
+    prefix sums 0/1 bytes with a dot product and must fall back to the exact count when it meets any other value."""
+    from leibnizgym_b200.config import difficulty_config
+    from leibnizgym_b200.env import TrifingerEnv
+    from leibnizgym_b200.sim import SyntheticSim
+    from leibnizgym_b200.synthetic import make_sequence
+    dev, N = "cuda:0", 8_192 + 77                       # 65 tiles, ragged last one -> direct prefix
+    ring = make_sequence(3, 2, N, device=dev)
+    env = TrifingerEnv(difficulty_config(2, N, asymmetric_obs=True, seed=3), device=dev, verbose=False,
+                       sim=SyntheticSim(ring, dev))
+    env.reset()
+    env.step(ring.action[0])                            # clears the initial all-reset
+    g = torch.Generator(device="cpu").manual_seed(11)
+    raw = torch.zeros(N, dtype=torch.uint8)
+    pick = torch.rand(N, generator=g) < 0.2
+    raw[pick] = torch.randint(1, 256, (int(pick.sum()),), generator=g, dtype=torch.int64).to(torch.uint8)
+    assert int((raw > 1).sum()) > 100
+    graw = torch.zeros(N, dtype=torch.uint8)
+    gpick = torch.rand(N, generator=g) < 0.1
+    graw[gpick] = 0x80
+    mask, gmask = raw.to(dev).view(torch.bool), graw.to(dev).view(torch.bool)
+    expected = torch.nonzero((raw != 0) | env._reset_buf.cpu().bool()).view(-1)
+    gexpected = torch.nonzero((graw != 0) | env._goal_reset_buf.cpu().bool()).view(-1)
+    env.set_forced_resets(mask, gmask)
+    env.step(ring.action[1])
+    torch.cuda.synchronize()
+    k, kg = int(env._counts[0]), int(env._counts[1])
+    assert k == expected.numel() and kg == gexpected.numel()
+    assert torch.equal(env._reset_ids[:k].cpu(), expected)
+    assert torch.equal(env._goal_reset_ids[:kg].cpu(), gexpected)
