@@ -405,7 +405,8 @@ def measure_device(args, wl, rank, world, local_rank, sampler=None):
     gmasks = bernoulli_masks(wl["seed"] + 7 + rank, R, N, wl.get("goal_p", 0.0), device=dev)
     env = TrifingerEnv(cfg, device=dev, verbose=False, sim=SyntheticSim(ring, dev), rank=rank, world_size=world)
     env.reset()
-    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks, inject_goal_masks=gmasks)
+    runner = GraphRunner(env, ring, rotate_outputs=True, inject_reset_masks=masks, inject_goal_masks=gmasks,
+                         chain_pre=not getattr(args, "no_chain", False))
     timer = DeviceTimer(world, dev)
     stream = torch.cuda.Stream()
     side = torch.cuda.Stream() if world > 1 else None
@@ -575,7 +576,10 @@ def run_gpu(args, wl):
                    "repeats": m["repeats"], "steps_per_graph": m["steps_per_graph"], "region_ms_median": m["region_ms"],
                    "us_per_step_median": m["us_per_step"], "us_per_step_p10": m["us_p10"], "us_per_step_p90": m["us_p90"],
                    "cold_start_us_per_step": m["cold_us_per_step"],
-                   "statistics_allreduce_in_region": world > 1},
+                   "statistics_allreduce_in_region": world > 1,
+                   "pre_launch": "stream order (lg_pre_physics)" if args.no_chain else
+                                 "chained to the preceding post-physics pass (lg_pre_physics_chained: actions and joint "
+                                 "states are resident in the ring long before they are used)"},
         "roofline": {"bound": "hbm", "kernel": "post_physics_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(N, asym), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": post_bytes, "launch_us": post_us,
@@ -713,6 +717,9 @@ def main():
                     help="also measure one line per BASELINE.json config (c1, c1sym, c2, c3ref, c4, c5) into `workloads`")
     ap.add_argument("--min-timed-ms", type=float, default=50.0, help="repeat the K-step region until this much device time is covered")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chain", action="store_true",
+                    help="launch the pre-physics pass in stream order (lg_pre_physics) instead of chained to the preceding "
+                         "post-physics pass (lg_pre_physics_chained)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-mode", default="copy", choices=["zc", "zc_out", "copy"])
     ap.add_argument("--e2e-chunks", type=int, default=1, help="env ranges of the host pipeline (0 = un-chunked copies)")

@@ -105,6 +105,7 @@ SYMBOLS = {
     "lg_pre_resident_tiles": (_i64, []),
     "lg_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "lg_pre_physics": (C.c_int, [_P, _S, _B, _vp, _vp]),
+    "lg_pre_physics_chained": (C.c_int, [_P, _S, _B, _vp, C.c_int, _vp]),
     "lg_post_physics": (C.c_int, [_P, _S, _B, C.c_double, _vp]),
     "lg_fill_observations": (C.c_int, [_P, _S, _B, _vp]),
     "lg_init_history": (C.c_int, [_P, _S, _B, _vp]),

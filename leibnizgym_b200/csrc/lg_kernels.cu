@@ -115,7 +115,10 @@ __global__ void selftest_division_kernel(float span, float rcp, unsigned long lo
 namespace {
 thread_local std::string g_error;
 int fail(int code, const std::string& msg) { g_error = msg; return code; }
+// What this thread launched last (lg_pre_physics_chained chains itself to a directly preceding lg_post_physics only).
+thread_local struct { void* stream; bool post; } g_prev = {nullptr, false};
 int check_launch(const char* what) {
+  g_prev.post = false;
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
   return LG_OK;
@@ -134,11 +137,10 @@ int sm_count() {
   return n;
 }
 
-// Programmatic dependent launch of the post-physics kernel (LG_PDL=0 / LG_NO_PDL=1 switch it off).  The pre-physics
-// kernel is always launched in stream order: launching it programmatically as well measured no gain without resets
-// and 21.6 instead of 17.5 us/step with 30 % resets in round 1 (a long pre-physics pass should not have the post
-// pass's CTAs parked on the SMs), and is not supported by the two-group kernel of round 2.
-int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : (env_int("LG_PDL", 2) & 2); return m; }
+// Programmatic dependent launch: bit 1 = the post-physics kernel after whatever precedes it, bit 0 = the pre-physics
+// kernel after a post-physics kernel, when the caller vouches for its inputs (lg_pre_physics_chained).  LG_PDL=0 /
+// LG_NO_PDL=1 switch both off, LG_PDL=2 the second.  lg_pre_physics itself is always launched in stream order.
+int pdl_mode() { static const int m = env_flag("LG_NO_PDL") ? 0 : (env_int("LG_PDL", 3) & 3); return m; }
 
 // Launch with programmatic stream serialisation (PDL) unless LG_NO_PDL is set.
 template <typename... KArgs, typename... Args>
@@ -233,7 +235,9 @@ int launch_post(const LgParams* P, const LgSimState* S, const LgBuffers* B, doub
 #endif
 #undef LG_X
   if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("post_physics_kernel: ") + cudaGetErrorString(err));
-  return check_launch("post_physics_kernel");
+  const int rc = check_launch("post_physics_kernel");
+  if (rc == LG_OK && REWARD) { g_prev.stream = (void*)st; g_prev.post = true; }
+  return rc;
 }
 }  // namespace
 
@@ -281,7 +285,9 @@ int lg_init_history(const LgParams* P, const LgSimState* S, const LgBuffers* B, 
   return check_launch("init_history_kernel");
 }
 
-int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in, void* stream) {
+namespace {
+int launch_pre(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in, void* stream,
+               bool chained, bool exclusive_sm) {
   if (int rc = validate(P, S, B, false)) return rc;
   if (!action_in) return fail(LG_ERR_BAD_ARG, "null action_in");
   if (!B->scan_status || !B->reset_ids || !B->goal_reset_ids || !B->counts)
@@ -318,8 +324,19 @@ cudaError_t err;
                       aligned16(B->reset) && aligned16(B->goal_reset) && aligned16(B->force_reset) &&
                       aligned16(B->force_goal_reset);
   const lg::PreHot hot = {action_in, S->dof_state, B->applied_torque, P->num_envs, tiles, 0};
-#define LG_PRE(AD, TK, MB, SP, DR) err = launch_pdl(false, lg::pre_physics_kernel<AD, TK, MB, SP, DR>, (unsigned)tiles, \
-                                                  SP ? lg::kPreThreads : lg::kScanThreads, 0, st, hot, *P, *S, *B)
+  // chained launch (lg_pre_physics_chained): optionally one CTA per SM, by 100 KB of unused dynamic shared memory
+  const bool pdl = chained && (pdl_mode() & 1) != 0;
+  const size_t dyn = (pdl && direct && exclusive_sm) ? 100 * 1024 : 0;
+  if (dyn) {
+    static const cudaError_t opt_in = [] {
+      cudaError_t a = cudaFuncSetAttribute(lg::pre_physics_kernel<9, false, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaError_t b = cudaFuncSetAttribute(lg::pre_physics_kernel<18, false, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      return a != cudaSuccess ? a : b;
+    }();
+    if (opt_in != cudaSuccess) return fail(LG_ERR_CUDA, std::string("pre_physics_kernel shared memory opt-in: ") + cudaGetErrorString(opt_in));
+  }
+#define LG_PRE(AD, TK, MB, SP, DR) err = launch_pdl(pdl, lg::pre_physics_kernel<AD, TK, MB, SP, DR>, (unsigned)tiles, \
+                                                  SP ? lg::kPreThreads : lg::kScanThreads, DR ? dyn : 0, st, hot, *P, *S, *B)
   if (P->action_dim == 9) {
     if (ticket) LG_PRE(9, true, 6, false, false); else if (direct) LG_PRE(9, false, 3, true, true);
     else if (small) LG_PRE(9, false, 3, true, false); else LG_PRE(9, false, 4, true, false);
@@ -328,7 +345,18 @@ cudaError_t err;
     else if (small) LG_PRE(18, false, 3, true, false); else LG_PRE(18, false, 4, true, false);
   }
 #undef LG_PRE
+  if (err != cudaSuccess) return fail(LG_ERR_CUDA, std::string("pre_physics_kernel: ") + cudaGetErrorString(err));
   return check_launch("pre_physics_kernel");
+}
+}  // namespace
+
+int lg_pre_physics(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in, void* stream) {
+  return launch_pre(P, S, B, action_in, stream, false, false);
+}
+int lg_pre_physics_chained(const LgParams* P, const LgSimState* S, const LgBuffers* B, const float* action_in,
+                           int exclusive_sm, void* stream) {
+  const bool after_post = g_prev.post && g_prev.stream == stream;
+  return launch_pre(P, S, B, action_in, stream, after_post, exclusive_sm != 0);
 }
 
 int lg_compact(const uint8_t* mask, int64_t n, int64_t* ids_out, int32_t* count_out, uint64_t* status,

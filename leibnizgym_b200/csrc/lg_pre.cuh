@@ -253,14 +253,16 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
   const bool row_group = !SPLIT || tid < kScanThreads;
   const bool scan_group = !SPLIT || tid >= kScanThreads;
   LG_TP(1, 0, tid == 0);
-  // Launched programmatically after lg_post_physics (see pdl_mode): what this kernel reads before pdl_wait() below
-  // must not be written by that kernel.  The control block (epoch, ticket) is only written by this kernel's own
-  // previous launch, the action and the joint state by the caller / simulator — all complete before the preceding
-  // post-physics pass was allowed past its own dependency wait.
-  // every thread reads the epoch before the tile publishes anything, so the last tile may advance it
-  const uint32_t epoch = ld_volatile_u32(&B.control->scan_epoch);
+  // May be launched programmatically after lg_post_physics (see pdl_mode): nothing the preceding kernel writes is read
+  // before pdl_wait() below — only the action and joint-state slabs, which the caller / simulator completed before that
+  // kernel was allowed past its own dependency wait.  The control block (epoch, ticket) is read after the wait: it is
+  // written by this kernel's own previous launch, which is not yet complete when two of these passes follow each other
+  // directly.
   int tile = blockIdx.x;
+  uint32_t epoch = 0;
   if (TICKET) {  // grids larger than what is co-resident: tiles by ticket, so predecessors always run
+    pdl_wait();
+    epoch = ld_volatile_u32(&B.control->scan_epoch);   // every thread, before the tile publishes anything (the last tile advances it)
     if (tid == 0) s_tile = (int)atomicAdd(&B.control->scan_ticket, 1u);
     __syncthreads();
     tile = s_tile;
@@ -291,7 +293,10 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
     }
   }
   LG_TP(1, 1, tid == 0);
-  pdl_wait();   // the flags, counters and statistics below are results of the preceding post-physics pass
+  if (!TICKET) {
+    pdl_wait();   // the flags, counters and statistics below are results of the preceding post-physics pass
+    epoch = ld_volatile_u32(&B.control->scan_epoch);   // every thread, before the tile publishes anything (the last tile advances it)
+  }
   LG_TP(1, 2, tid == 0);
   uint32_t before = 0;   // DIRECT: this thread's share of the flagged envs in front of the tile (a | b << 16)
   if (DIRECT) before = count_flagged_before(B.reset, B.goal_reset, B.force_reset, B.force_goal_reset, tile * (E / 16), tid);

@@ -28,7 +28,7 @@ from .synthetic import StateSequence
 class GraphRunner:
     def __init__(self, env: TrifingerEnv, ring: StateSequence, rotate_outputs: bool = True,
                  inject_reset_masks: Optional[torch.Tensor] = None, device_clock: bool = True,
-                 inject_goal_masks: Optional[torch.Tensor] = None):
+                 inject_goal_masks: Optional[torch.Tensor] = None, chain_pre: bool = True):
         assert ring.dof_state.is_cuda, "the ring must be device resident"
         self.env, self.ring = env, ring
         self.R = ring.num_steps
@@ -41,6 +41,11 @@ class GraphRunner:
         # itself (LgBuffers.force_reset / force_goal_reset) — no separate pass over the flags
         self.reset_masks = inject_reset_masks
         self.goal_masks = inject_goal_masks
+        # The runner's actions and joint states sit in the ring long before they are used: the contract of
+        # lg_pre_physics_chained holds, so the pre-physics pass of step t+1 is chained to the post-physics pass of step
+        # t.  With injected reset masks (reset-heavy workloads) each of its CTAs gets an SM of its own.
+        self.chain_pre = chain_pre
+        self.exclusive_sm = int(inject_reset_masks is not None)
         self.P = nat.LgParams.from_buffer_copy(env._P)
         self.P.use_device_clock = int(device_clock)
         self.P.fuse_bookkeeping = 1
@@ -77,8 +82,12 @@ class GraphRunner:
         prev = (t - 1) % self.R
         if not post_only:
             # resets write into the tensors the simulator consumes next (slot of the previous state)
-            nat.check(self.lib.lg_pre_physics(self.P, self._S[prev], self._B[prev],
-                                              self.ring.action[s].data_ptr(), stream), "lg_pre_physics")
+            if self.chain_pre:
+                nat.check(self.lib.lg_pre_physics_chained(self.P, self._S[prev], self._B[prev], self.ring.action[s].data_ptr(),
+                                                          self.exclusive_sm, stream), "lg_pre_physics_chained")
+            else:
+                nat.check(self.lib.lg_pre_physics(self.P, self._S[prev], self._B[prev],
+                                                  self.ring.action[s].data_ptr(), stream), "lg_pre_physics")
         if pre_only:
             return
         sched = 0.0 if self.device_clock else float((self.frame0 + (t - self.t0) + 1) * self.env._global_N)

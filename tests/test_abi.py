@@ -22,7 +22,7 @@ def test_library_builds_and_loads():
     assert os.path.exists(path)
     from leibnizgym_b200 import _native
     lib = _native.load()
-    assert lib.lg_version() == 110
+    assert lib.lg_version() == 111
 
 
 def test_every_declared_symbol_is_exported_and_bound():
