@@ -6,7 +6,7 @@
 
 The -DLG_TRACE build stamps %globaltimer at named points of pre_physics_kernel / post_physics_kernel (lane 0 of
 selected warps, every CTA).  This script replays a graph of consecutive steps, reads the stamps of the LAST launch of
-each kernel and prints, per point, when it was reached relative to the first CTA's entry: min / median / max over the
+each kernel and prints, per point, when it was reached relative to the first CTA's entry: min / median / p90 / max over the
 CTAs.  The step time from CUDA events next to it tells how much of a step is the gap between kernels.
 """
 import argparse
@@ -49,10 +49,10 @@ def read_trace(lib, which, ctas):
 
 def show(name, names, t, t_ref=None):
     t0 = t[:, 0].min() if t_ref is None else t_ref
-    print(f"--- {name}: {t.shape[0]} CTAs; ns after the first CTA's entry (min / median / max over CTAs)")
+    print(f"--- {name}: {t.shape[0]} CTAs; ns after the first CTA's entry (min / median / p90 / max over CTAs)")
     for slot in sorted(names, key=lambda s: np.median(t[:, s])):
         col = t[:, slot] - t0
-        print(f"  {names[slot]:<32s} {col.min():7d} {int(np.median(col)):7d} {col.max():7d}")
+        print(f"  {names[slot]:<32s} {col.min():7d} {int(np.median(col)):7d} {int(np.percentile(col, 90)):7d} {col.max():7d}")
     return t0
 
 
