@@ -570,10 +570,10 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   const uint8_t* p_reset = B.reset + e0 + renv;
   const int64_t* p_steps = B.steps_count + e0 + renv;
   asm volatile("" : "+l"(hist_src), "+l"(p_goal_reset), "+l"(p_succ), "+l"(p_reset), "+l"(p_steps), "+l"(src));
-  if (P.normalize_obs && dcol >= 0) {
+  if (P.normalize_obs && dcol >= 0) {   // fetched here, used (and halved / doubled) only after the tile's loads are issued
     centre = __ldg(B.scale_table + dcol);
-    half_span = 0.5f * __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
-    rcp_half = 2.0f * __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
+    half_span = __ldg(B.scale_table + LG_MAX_STATE_DIM + dcol);
+    rcp_half = __ldg(B.scale_table + 2 * LG_MAX_STATE_DIM + dcol);
   }
   if (!(REWARD && P.use_device_clock) && tid < C_COUNT) s_coef[tid] = CF.v[tid];
   pdl_wait();  // everything above is independent of the previous kernel's results
@@ -583,10 +583,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   float4 hprev = make_float4(0.f, 0.f, 0.f, 0.f);
   uint8_t in_goal_reset = 0, in_succ = 0, in_reset = 0;
   int64_t in_steps = 0;
-  if (rlive) {
-    hprev = ld_hist4(hist_src);
-    if (rw == kCombineWarp) { in_goal_reset = *p_goal_reset; in_succ = *p_succ; in_reset = *p_reset; in_steps = *p_steps; }
-  }
+  if (rlive) hprev = ld_hist4(hist_src);
   float v[EP];
   if (full) {
 #pragma unroll
@@ -595,7 +592,16 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < EP; ++k) v[k] = k < cnt ? ld_stream1(src + (int64_t)k * stride) : 0.0f;
   }
+  // The flags and the step counter are needed last (by the combine): fetched after the tile's loads.  In front of them
+  // the compiler turned the flag bytes into predicates at once — a full round trip in which the combine warp had not
+  // yet issued its column loads.
+  asm volatile("" : "+l"(p_goal_reset), "+l"(p_succ), "+l"(p_reset), "+l"(p_steps));
+  if (rlive && rw == kCombineWarp) { in_goal_reset = *p_goal_reset; in_succ = *p_succ; in_reset = *p_reset; in_steps = *p_steps; }
   pdl_launch_dependents();  // the next kernel may start launching; it still waits for this grid to finish
+  // same for the scale constants: a CTA that starts late must not wait for them before it has issued its loads
+  asm volatile("" : "+f"(half_span), "+f"(rcp_half));
+  half_span = 0.5f * half_span;
+  rcp_half = 2.0f * rcp_half;
   LG_TP(0, 2, tid == 0);
 
   // ---- reward coefficients: from the launch arguments, or (device clock) from what lg_pre_physics wrote ----

@@ -298,6 +298,14 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
     epoch = ld_volatile_u32(&B.control->scan_epoch);   // every thread, before the tile publishes anything (the last tile advances it)
   }
   LG_TP(1, 2, tid == 0);
+  // scan group: this env's own flag bytes, fetched FIRST — in the same round trip as (DIRECT) the predecessors' bytes,
+  // not after they have been counted
+  uint8_t flag_r = 0, flag_g = 0, flag_fr = 0, flag_fg = 0;
+  if (scan_group && live) {
+    flag_r = B.reset[e]; flag_g = B.goal_reset[e];
+    if (B.force_reset) flag_fr = B.force_reset[e];             // `_reset_buf |= mask` folded into the pass
+    if (B.force_goal_reset) flag_fg = B.force_goal_reset[e];
+  }
   uint32_t before = 0;   // DIRECT: this thread's share of the flagged envs in front of the tile (a | b << 16)
   if (DIRECT) before = count_flagged_before(B.reset, B.goal_reset, B.force_reset, B.force_goal_reset, tile * (E / 16), tid);
 
@@ -308,13 +316,7 @@ pre_physics_kernel(const __grid_constant__ PreHot H, const __grid_constant__ LgP
   t.tile = tile; t.epoch = epoch;
   bool f_reset = false, f_goal = false;
   if (scan_group) {
-    uint8_t flag_r = 0, flag_g = 0;
-    if (live) {
-      flag_r = B.reset[e]; flag_g = B.goal_reset[e];
-      if (B.force_reset) flag_r |= B.force_reset[e];             // `_reset_buf |= mask` folded into the pass
-      if (B.force_goal_reset) flag_g |= B.force_goal_reset[e];
-    }
-    f_reset = flag_r != 0; f_goal = flag_g != 0;
+    f_reset = (flag_r | flag_fr) != 0; f_goal = (flag_g | flag_fg) != 0;
     tile_scan_local<1>(f_reset, f_goal, gt, s_wa, s_wb, t);
     s_flag[gt] = (uint8_t)((f_reset ? 1 : 0) | (f_goal ? 2 : 0));
     if (f_reset) s_reset_list[t.rank_a] = (uint16_t)(gt | (f_goal ? 0x8000 : 0));   // flagged envs by rank in the tile
