@@ -542,7 +542,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   int hist_col = -1;            // column of the NEXT history entry this lane provides, or -1
   // this lane's scale_transform constants (torch_utils.py:33-36) in half-span form:
   // 2 (x - c) / span == (x - c) / (span / 2), both scalings exact.  normalize_obs = False: x / 1.
-  float centre = 0.0f, half_span = 1.0f, rcp_half = 1.0f;
+  float centre = 0.0f, half_span = 2.0f, rcp_half = 0.5f;   // span and 1 / span; halved / doubled below (x / 1 when raw)
   {
     const RoleInfo r = role_info<A, ASYM>(P, role);
     const int src_id = r.src_id, src_off = r.src_off, stage_id = r.stage_id, stage_off = r.stage_off;
