@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LG_VERSION 111            /* 1.1.0 */
+#define LG_VERSION 111            /* 1.1.1 */
 #define LG_MAX_ACTION_DIM 18      /* position_impedance: 9 positions + 9 stiffnesses */
 #define LG_MAX_STATE_DIM 122      /* 50 + 6 + 39 + 9 + 18 */
 #define LG_NUM_TERMS 7            /* six reference terms + the keypoint extension */
