@@ -1,5 +1,6 @@
-// pre-physics pass of the TriFinger MDP hot path (sm_100a): ordered mask compaction (decoupled look-back) fused with
-// reset / goal-reset sampling and scatter, action store and action -> torque; tile slabs by TMA bulk copy.
+// pre-physics pass of the TriFinger MDP hot path (sm_100a): ordered mask compaction (decoupled look-back, or a direct
+// count of the flag bytes for one-wave grids) fused with reset / goal-reset sampling and scatter, action store and
+// action -> torque; tile slabs by TMA bulk copy.
 // Also the stand-alone compaction and the hook kernels on explicit id lists.
 // Included by lg_kernels.cu (single translation unit).  Reference paths are relative to /root/reference/leibnizgym/.
 #pragma once
@@ -217,12 +218,16 @@ struct PreHot {
 //   scan group (warps 4-7, thread = env): flag bytes -> ballot/popcount block scan of both masks -> aggregate
 //              published -> block-wide decoupled look-back -> ascending id lists (torch.nonzero order) and the
 //              simulator's actor-index lists.
-// They meet for the resets (block-uniform branch: eight reset sub-tasks over the eight warps, lane = listed env);
-// the row group then computes the torque from the shared-memory slabs while the scan group resolves its look-back;
-// action and torque rows leave as bulk stores.
+// They meet for the resets (block-uniform branch: ten reset sub-tasks as work items over the eight warps, lane =
+// listed env); the row group then computes the torque from the shared-memory slabs while the scan group resolves its
+// look-back; action and torque rows leave as bulk stores.
 // MINB = CTAs per SM the register allocation must allow: 3 (<= 85 registers) for grids of one wave, where
 // the kernel is a latency chain (30 % resets at 16 384 envs: 17.3 against 18.0 us/step), 4 (64 registers) for larger
 // grids, where more rows in flight per SM is what counts (65 536 envs with goal resampling: 37.7 against 42.3 us/step).
+//
+// DIRECT (grids of 32 .. kDirectMaxTiles tiles, one CTA per SM): no look-back — every tile counts the flagged envs in
+// front of it itself (count_flagged_before above), so no tile waits for another one's progress; the only grid-wide
+// hand-shake left protects the clearing of flag bytes by tiles with resets (scan_readers / scan_exits, below).
 //
 // SPLIT = false is the same pass with ONE 128-thread group doing both chains one after the other (look-back last, when
 // every predecessor has long published): grids of many waves are bound by the rows in flight per SM, not by the length
