@@ -226,7 +226,7 @@ __device__ __forceinline__ RoleInfo role_info(const LgParams& P, int role) {
 
 // Statistics in fixed point (see reward_combine): scale 2^30, values must stay below 2^28 so that 32 of them fit int64.
 constexpr float kStatFixScale = 1073741824.0f, kStatFixMax = 268435456.0f;
-// What a statistics lane multiplies its integer sum by: lane s of warp 0 owns slot s.  Reward-term, reward and success
+// What a statistics lane multiplies its integer sum by: lane s of the combine warp owns slot s.  Reward-term, reward and success
 // entries are means over this shard (trifinger_env.py:554, :1098), the rest are counts (:1067, :1076).  Evaluated in
 // the kernel prologue (an fp64 division is a chain of ~10 dependent fp64 operations, each ~0.1-0.2 us for a lone warp
 // on this part).  When the env count is a power of two the factor is one too and only its exponent is kept: the
@@ -358,7 +358,7 @@ __device__ __forceinline__ void reward_subtasks(const LgParams& P, int nvalid,
       }
       // extension (no reference code): keypoint pose reward
       //   w dt mean_k lgsk(|kp_k - kp_k^goal|; scale, eps), kp_k = p + R(q) c_k over the 8 cube corners;
-      // two corners per reward warp, summed by warp 0
+      // two corners per reward warp, summed by the combine warp
       if (EXT && ((P.term_active_mask >> LG_TERM_KEYPOINT) & 1)) {
         const Quat oq{obj[3], obj[4], obj[5], obj[6]};
         const Quat gq{goal[3], goal[4], goal[5], goal[6]};
@@ -556,7 +556,7 @@ post_physics_kernel(const __grid_constant__ LgParams P, const __grid_constant__ 
   const int cnt = max(0, min(EP, nvalid - env_first));   // envs of this lane: env_first .. env_first + cnt - 1
   const bool full = nvalid == E;                                  // every CTA but possibly the last
   // reward warps: thread (w, env) = (tid / 32, tid % 32), w < 4.  Each fetches one 16-byte piece of the
-  // env's previous history entry (64-byte rows), warp 0 also the env's flags and step counter.
+  // env's previous history entry (64-byte rows), the combine warp also the env's flags and step counter.
   const int rw = tid >> 5, renv = tid & 31;
   const bool rlive = REWARD && rw < 4 && renv < nvalid;
   // Everything the first instructions after the dependency wait need is resolved BEFORE it: kernel parameters sit in
